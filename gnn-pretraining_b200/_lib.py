@@ -1,0 +1,71 @@
+"""ctypes binding of libgnnb200.so (the C ABI declared in include/gnnb200.h).
+
+There is no CPU or eager fallback: if the shared library is missing, loading fails loudly.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libgnnb200.so')
+
+OK, EINVAL, ERANGE, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
+AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
+POOL_SUM, POOL_MEAN, POOL_MAX = 0, 1, 2
+GEMM_F32, GEMM_TF32 = 0, 1
+EPI_NONE, EPI_RELU = 0, 1
+
+P = c_void_p
+I64 = c_int64
+SZP = POINTER(c_size_t)
+
+# name -> argtypes, in the order of include/gnnb200.h
+SIGNATURES = {
+    'gnnb200_version': [],
+    'gnnb200_error_string': [c_int],
+    'gnnb200_csr_build_i64': [P, I64, I64, c_int, P, P, P, P, SZP, P],
+    'gnnb200_segment_ptr_i64': [P, I64, I64, P, P],
+    'gnnb200_coalesce_i64': [P, I64, I64, P, P, P, SZP, P],
+    'gnnb200_aggregate_f32': [P, I64, P, P, I64, I64, c_int, P, I64, P, P, P, I64, P],
+    'gnnb200_dot_f32': [P, P, I64, P, P, SZP, P],
+    'gnnb200_segment_pool_fwd_f32': [P, I64, P, I64, I64, I64, c_int, P, I64, P, SZP, P],
+    'gnnb200_segment_pool_bwd_f32': [P, I64, P, I64, P, I64, P, I64, I64, I64, c_int, P, I64, P],
+    'gnnb200_rows_gather_f32': [P, I64, P, I64, I64, P, I64, P],
+    'gnnb200_rows_scatter_f32': [P, I64, c_int, P, I64, I64, P, I64, P],
+    'gnnb200_rows_gather_bwd_f32': [P, I64, P, P, I64, I64, P, I64, P],
+    'gnnb200_gemm_f32': [P, I64, c_int, P, I64, c_int, P, I64, I64, I64, I64, P, c_int, c_int, P, SZP, P],
+    'gnnb200_colstats_f32': [P, I64, I64, I64, P, P, P, SZP, P],
+    'gnnb200_lp_features_f32': [P, I64, P, I64, I64, P, I64, P],
+    'gnnb200_lp_features_bwd_f32': [P, I64, P, I64, I64, P, I64, P, P, P, P, I64, P, I64, P],
+    'gnnb200_ntxent_fwd_f32': [P, I64, I64, I64, c_float, P, P, P, P, P, SZP, P],
+    'gnnb200_ntxent_bwd_f32': [P, P, P, P, I64, I64, c_float, P, I64, P],
+}
+
+_lib = None
+
+
+class Gnnb200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise Gnnb200Error(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU / eager fallback for the gnnb200 hot path)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError -> header and library disagree
+        fn.argtypes = argtypes
+        fn.restype = c_char_p if name == 'gnnb200_error_string' else c_int
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().gnnb200_error_string(code).decode()
+        raise Gnnb200Error(f'{what} failed: {msg} (code {code})')

@@ -1,0 +1,76 @@
+"""Sorted-CSR view of an ``edge_index`` tensor, built on the device once and reused by every layer
+and every pass that sees the same tensor (the reference rebuilds nothing because it has no CSR;
+SURVEY.md §8a row a4)."""
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+_ATTR = '_gnnb200_graph'
+
+
+class Graph:
+    """rowptr/col grouped by destination (forward gather) and, lazily, rowptr_t/col_t grouped by
+    source (backward gather).  Within a row, neighbours keep the original edge order, which makes
+    the fp32 sums bit-identical to the CPU scatter_add_ order."""
+
+    def __init__(self, edge_index: Tensor, num_nodes: int):
+        self.edge_index = edge_index
+        self.num_nodes = int(num_nodes)
+        self.num_edges = int(edge_index.size(1))
+        self.rowptr, self.col, self.eid = ops.csr_build(edge_index, self.num_nodes, False)
+        self._t = None
+        self._version = edge_index._version
+
+    def transposed(self):
+        if self._t is None:
+            self._t = ops.csr_build(self.edge_index, self.num_nodes, True)
+        return self._t
+
+    @property
+    def rowptr_t(self) -> Tensor:
+        return self.transposed()[0]
+
+    @property
+    def col_t(self) -> Tensor:
+        return self.transposed()[1]
+
+    def in_degree(self) -> Tensor:
+        return (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+
+    def out_degree(self) -> Tensor:
+        r = self.rowptr_t
+        return (r[1:] - r[:-1]).to(torch.int64)
+
+
+def graph_of(edge_index: Tensor, num_nodes: int) -> Graph:
+    """Cached Graph for this edge_index tensor object (invalidated by in-place edits)."""
+    g: Optional[Graph] = getattr(edge_index, _ATTR, None)
+    if g is not None and g.num_nodes == num_nodes and g._version == edge_index._version \
+            and g.num_edges == edge_index.size(1):
+        return g
+    g = Graph(edge_index, num_nodes)
+    try:
+        setattr(edge_index, _ATTR, g)
+    except AttributeError:
+        pass
+    return g
+
+
+def segment_ptr_of(batch: Tensor, size: Optional[int] = None) -> Tensor:
+    """int32 ptr [B+1] for a sorted ``batch`` vector, cached on the tensor object.  When ``size`` is
+    not given it is read from the last element (one device->host sync, like PyG's
+    ``int(batch.max()) + 1``)."""
+    cached = getattr(batch, '_gnnb200_ptr', None)
+    if cached is not None and cached[1] == batch._version and (size is None or cached[0].numel() == size + 1):
+        return cached[0]
+    if size is None:
+        size = int(batch[-1]) + 1 if batch.numel() > 0 else 0
+    ptr = ops.segment_ptr(batch, size)
+    try:
+        setattr(batch, '_gnnb200_ptr', (ptr, batch._version))
+    except AttributeError:
+        pass
+    return ptr

@@ -1,0 +1,109 @@
+"""Drop-in message-passing primitives with the call signatures of the PyG names the reference
+imports (`from torch_geometric.nn import GINConv, global_mean_pool, global_max_pool`,
+reference src/models/gnn.py:4, src/models/finetune_model.py:7, src/pretrain/tasks.py:9), backed by
+the gnnb200 CUDA kernels."""
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+from .graph import graph_of, segment_ptr_of
+
+# Default arithmetic of the dense transforms: 'f32' (FFMA, 1e-5 class) or 'tf32' (tcgen05, 2e-2 class).
+_default_precision = 'f32'
+
+
+def set_default_precision(name: str) -> None:
+    global _default_precision
+    if name not in ops.PRECISIONS:
+        raise ValueError(f'unknown precision {name!r}')
+    _default_precision = name
+
+
+def default_precision() -> str:
+    return _default_precision
+
+
+class Linear(torch.nn.Linear):
+    """nn.Linear whose forward/backward GEMMs run on the gnnb200 kernels (same parameters/keys)."""
+
+    precision: Optional[str] = None
+
+    def forward(self, x: Tensor) -> Tensor:
+        prec = ops.PRECISIONS[self.precision or _default_precision]
+        lead = x.shape[:-1]
+        y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec)
+        return y.view(*lead, self.out_features)
+
+
+class SumAggregation(torch.nn.Module):
+    """Parameter-free child kept so that reference checkpoints (which list `gin_conv.aggr_module`)
+    load with strict key matching."""
+
+    def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
+        g = graph_of(edge_index, x.size(0))
+        return ops.aggregate(x, g.rowptr, g.col, L.AGG_SUM)
+
+
+def _reset(module: torch.nn.Module) -> None:
+    if hasattr(module, 'reset_parameters'):
+        module.reset_parameters()
+    else:
+        for child in module.children():
+            _reset(child)
+
+
+class GINConv(torch.nn.Module):
+    """out = nn( sum_{j->i} x_j + (1 + eps) * x_i )  — PyG GINConv(nn, eps, train_eps) semantics
+    (SURVEY.md App. A.1), one fused CSR gather kernel for the sum and the self term."""
+
+    def __init__(self, nn: torch.nn.Module, eps: float = 0.0, train_eps: bool = False, **kwargs):
+        super().__init__()
+        self.aggr_module = SumAggregation()
+        self.nn = nn
+        self.initial_eps = float(eps)
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.empty(1))
+        else:
+            self.register_buffer('eps', torch.empty(1))
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        _reset(self.nn)
+        self.eps.data.fill_(self.initial_eps)
+
+    def aggregate(self, x: Tensor, edge_index: Tensor) -> Tensor:
+        g = graph_of(edge_index, x.size(0))
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or self.eps.requires_grad)
+        if needs_grad:
+            rowptr_t, col_t = g.rowptr_t, g.col_t
+        else:
+            rowptr_t = col_t = g.rowptr.new_empty(0)
+        return ops.gin_aggregate(x, self.eps, g.rowptr, g.col, rowptr_t, col_t)
+
+    def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
+        return self.nn(self.aggregate(x, edge_index))
+
+
+def _pool(x: Tensor, batch: Optional[Tensor], size: Optional[int], mode: int) -> Tensor:
+    if batch is None:
+        ptr = torch.tensor([0, x.size(0)], dtype=torch.int32, device=x.device)
+    else:
+        ptr = segment_ptr_of(batch, size)
+    return ops.segment_pool(x, ptr, mode)
+
+
+def global_mean_pool(x: Tensor, batch: Optional[Tensor], size: Optional[int] = None) -> Tensor:
+    """Per-graph mean (empty graphs -> 0).  ``batch`` must be sorted (PyG Batch guarantees it)."""
+    return _pool(x, batch, size, L.POOL_MEAN)
+
+
+def global_max_pool(x: Tensor, batch: Optional[Tensor], size: Optional[int] = None) -> Tensor:
+    """Per-graph channel-wise max with torch's native amax gradient rule."""
+    return _pool(x, batch, size, L.POOL_MAX)
+
+
+def global_add_pool(x: Tensor, batch: Optional[Tensor], size: Optional[int] = None) -> Tensor:
+    return _pool(x, batch, size, L.POOL_SUM)

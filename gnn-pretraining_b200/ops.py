@@ -1,0 +1,559 @@
+"""torch.library custom ops (namespace ``gnnb200``) over the C ABI of libgnnb200.so.
+
+Each op takes CUDA tensors, hands raw device pointers + the current CUDA stream to one
+``gnnb200_*`` entry point (include/gnnb200.h) and returns fresh tensors.  Autograd formulas are
+registered here too; every backward is itself made of gnnb200 ops (the transposed-CSR gather for
+the aggregation, the amax-rule scatter for max pooling, GEMMs for the linears).  There is no CPU
+or eager fallback: CPU tensors raise.
+"""
+import ctypes
+from ctypes import byref, c_size_t
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = L.load()
+    return _lib
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*tensors: Optional[Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise L.Gnnb200Error('gnnb200 ops run on CUDA tensors only (no CPU fallback)')
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    """2-D fp32 with unit inner stride (any leading dimension)."""
+    if t.dtype != torch.float32:
+        raise L.Gnnb200Error(f'expected float32, got {t.dtype}')
+    if t.dim() != 2:
+        raise L.Gnnb200Error(f'expected a 2-D tensor, got {t.dim()}-D')
+    if t.size(1) > 1 and t.stride(1) != 1:
+        return t.contiguous()
+    if t.size(0) > 1 and t.stride(0) < t.size(1):      # expanded / overlapping rows
+        return t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+
+
+def _call_ws(fn, what: str, device, *args, stream: int):
+    """Two-phase call of an entry point whose trailing args are (workspace, &bytes, stream)."""
+    need = c_size_t(0)
+    L.check(fn(*args, None, byref(need), stream), what + ' (workspace query)')
+    ws = torch.empty(max(int(need.value), 256), dtype=torch.uint8, device=device)
+    have = c_size_t(ws.numel())
+    L.check(fn(*args, ws.data_ptr(), byref(have), stream), what)
+    return ws
+
+
+# ---------------------------------------------------------------------------------------------
+# structure ops (integer, bit-exact)
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('gnnb200::csr_build', mutates_args=())
+def csr_build(edge_index: Tensor, num_nodes: int, by_src: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """(rowptr int32 [N+1], col int32 [E], eid int32 [E]); see gnnb200_csr_build_i64."""
+    _need_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise L.Gnnb200Error('edge_index must be int64 [2, E]')
+    ei = edge_index.contiguous()
+    E = ei.size(1)
+    dev = ei.device
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    eid = torch.empty(E, dtype=torch.int32, device=dev)
+    _call_ws(lib().gnnb200_csr_build_i64, 'csr_build', dev, _ptr(ei), E, num_nodes, int(by_src),
+             _ptr(rowptr), _ptr(col), _ptr(eid), stream=_stream(ei))
+    return rowptr, col, eid
+
+
+@csr_build.register_fake
+def _(edge_index, num_nodes, by_src):
+    E = edge_index.size(1)
+    mk = lambda n: edge_index.new_empty(n, dtype=torch.int32)
+    return mk(num_nodes + 1), mk(E), mk(E)
+
+
+@torch.library.custom_op('gnnb200::segment_ptr', mutates_args=())
+def segment_ptr(ids: Tensor, num_segments: int) -> Tensor:
+    """Offsets int32 [S+1] of a sorted int64 id vector (Batch.batch -> ptr)."""
+    _need_cuda(ids)
+    ids = ids.contiguous()
+    out = torch.empty(num_segments + 1, dtype=torch.int32, device=ids.device)
+    L.check(lib().gnnb200_segment_ptr_i64(_ptr(ids), ids.numel(), num_segments, _ptr(out), _stream(ids)),
+            'segment_ptr')
+    return out
+
+
+@segment_ptr.register_fake
+def _(ids, num_segments):
+    return ids.new_empty(num_segments + 1, dtype=torch.int32)
+
+
+@torch.library.custom_op('gnnb200::coalesce', mutates_args=())
+def coalesce(edge_index: Tensor, num_nodes: int) -> Tuple[Tensor, Tensor]:
+    """(out [2, E] capacity buffer, count int64 [1]): columns sorted by row*N+col, duplicates dropped."""
+    _need_cuda(edge_index)
+    ei = edge_index.contiguous()
+    E = ei.size(1)
+    out = torch.empty_like(ei)
+    count = torch.zeros(1, dtype=torch.int64, device=ei.device)
+    _call_ws(lib().gnnb200_coalesce_i64, 'coalesce', ei.device, _ptr(ei), E, num_nodes, _ptr(out), _ptr(count),
+             stream=_stream(ei))
+    return out, count
+
+
+@coalesce.register_fake
+def _(edge_index, num_nodes):
+    return torch.empty_like(edge_index), edge_index.new_empty(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# aggregation
+# ---------------------------------------------------------------------------------------------
+def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Optional[Tensor],
+                   eps: Optional[Tensor], dinv: Optional[Tensor]) -> Tensor:
+    _need_cuda(x, rowptr, col, self_x, eps, dinv)
+    x = _rowmajor(x)
+    n_rows = rowptr.numel() - 1
+    out = torch.empty(n_rows, x.size(1), dtype=torch.float32, device=x.device)
+    if self_x is not None:
+        self_x = _rowmajor(self_x)
+    L.check(lib().gnnb200_aggregate_f32(
+        _ptr(x), _ld(x), _ptr(rowptr), _ptr(col), n_rows, x.size(1), mode,
+        _ptr(self_x), _ld(self_x) if self_x is not None else 0, _ptr(eps), _ptr(dinv),
+        _ptr(out), _ld(out), _stream(x)), 'aggregate')
+    return out
+
+
+@torch.library.custom_op('gnnb200::aggregate', mutates_args=())
+def aggregate(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Optional[Tensor] = None,
+              eps: Optional[Tensor] = None, dinv: Optional[Tensor] = None) -> Tensor:
+    """Raw CSR aggregation (no autograd): see gnnb200_aggregate_f32."""
+    return _aggregate_raw(x, rowptr, col, mode, self_x, eps, dinv)
+
+
+@aggregate.register_fake
+def _(x, rowptr, col, mode, self_x=None, eps=None, dinv=None):
+    return x.new_empty(rowptr.numel() - 1, x.size(1))
+
+
+@torch.library.custom_op('gnnb200::dot', mutates_args=())
+def dot(a: Tensor, b: Tensor) -> Tensor:
+    """Deterministic sum(a*b) -> [1]."""
+    _need_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    _call_ws(lib().gnnb200_dot_f32, 'dot', a.device, _ptr(a), _ptr(b), a.numel(), _ptr(out), stream=_stream(a))
+    return out
+
+
+@dot.register_fake
+def _(a, b):
+    return a.new_empty(1)
+
+
+@torch.library.custom_op('gnnb200::gin_aggregate', mutates_args=())
+def gin_aggregate(x: Tensor, eps: Tensor, rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor) -> Tensor:
+    """z[i] = sum_{e: dst=i} x[src_e] + (1+eps) * x[i]   (GINConv before its MLP).
+    rowptr/col: CSR grouped by dst; rowptr_t/col_t: grouped by src (used by the backward)."""
+    return _aggregate_raw(x, rowptr, col, L.AGG_SUM, x, eps, None)
+
+
+@gin_aggregate.register_fake
+def _(x, eps, rowptr, col, rowptr_t, col_t):
+    return torch.empty_like(x)
+
+
+def _gin_setup(ctx, inputs, output):
+    x, eps, rowptr, col, rowptr_t, col_t = inputs
+    ctx.save_for_backward(x, eps, rowptr, col, rowptr_t, col_t)
+
+
+def _gin_backward(ctx, g):
+    x, eps, rowptr, col, rowptr_t, col_t = ctx.saved_tensors
+    g = g.contiguous()
+    gx = geps = None
+    if ctx.needs_input_grad[0]:
+        if rowptr_t.numel() == 0:
+            raise L.Gnnb200Error('gin_aggregate backward needs the by-src CSR (build the graph with grad enabled)')
+        gx = gin_aggregate(g, eps, rowptr_t, col_t, rowptr, col)   # transposed gather + (1+eps) g
+    if ctx.needs_input_grad[1]:
+        geps = dot(g, x)                                          # d/d eps = sum(g * x)
+    return gx, geps, None, None, None, None
+
+
+gin_aggregate.register_autograd(_gin_backward, setup_context=_gin_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('gnnb200::segment_pool', mutates_args=())
+def segment_pool(x: Tensor, ptr: Tensor, mode: int) -> Tensor:
+    """Segment sum/mean/max over row ranges ptr (int32 [S+1]) -> [S, F]."""
+    _need_cuda(x, ptr)
+    x = _rowmajor(x)
+    S = ptr.numel() - 1
+    out = torch.empty(S, x.size(1), dtype=torch.float32, device=x.device)
+    _call_ws(lib().gnnb200_segment_pool_fwd_f32, 'segment_pool', x.device, _ptr(x), _ld(x), _ptr(ptr), x.size(0), S,
+             x.size(1), mode, _ptr(out), _ld(out), stream=_stream(x))
+    return out
+
+
+@segment_pool.register_fake
+def _(x, ptr, mode):
+    return x.new_empty(ptr.numel() - 1, x.size(1))
+
+
+@torch.library.custom_op('gnnb200::segment_pool_bwd', mutates_args=())
+def segment_pool_bwd(grad_out: Tensor, x: Tensor, out: Tensor, ptr: Tensor, mode: int) -> Tensor:
+    _need_cuda(grad_out, x, out, ptr)
+    g, x, out = _rowmajor(grad_out), _rowmajor(x), _rowmajor(out)
+    S = ptr.numel() - 1
+    gx = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
+    L.check(lib().gnnb200_segment_pool_bwd_f32(
+        _ptr(g), _ld(g), _ptr(x), _ld(x), _ptr(out), _ld(out), _ptr(ptr), x.size(0), S, x.size(1), mode,
+        _ptr(gx), _ld(gx), _stream(x)), 'segment_pool_bwd')
+    return gx
+
+
+@segment_pool_bwd.register_fake
+def _(grad_out, x, out, ptr, mode):
+    return torch.empty_like(x)
+
+
+def _pool_setup(ctx, inputs, output):
+    x, ptr, mode = inputs
+    ctx.mode = mode
+    ctx.save_for_backward(x, output, ptr)
+
+
+def _pool_backward(ctx, g):
+    x, out, ptr = ctx.saved_tensors
+    return segment_pool_bwd(g.contiguous(), x, out, ptr, ctx.mode), None, None
+
+
+segment_pool.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# row gather / scatter
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('gnnb200::rows_gather', mutates_args=())
+def rows_gather(x: Tensor, idx: Tensor) -> Tensor:
+    """out[i] = x[idx[i]] (idx int64)."""
+    _need_cuda(x, idx)
+    x = _rowmajor(x)
+    idx = idx.contiguous()
+    out = torch.empty(idx.numel(), x.size(1), dtype=torch.float32, device=x.device)
+    L.check(lib().gnnb200_rows_gather_f32(_ptr(x), _ld(x), _ptr(idx), idx.numel(), x.size(1), _ptr(out), _ld(out),
+                                         _stream(x)), 'rows_gather')
+    return out
+
+
+@rows_gather.register_fake
+def _(x, idx):
+    return x.new_empty(idx.numel(), x.size(1))
+
+
+@torch.library.custom_op('gnnb200::rows_gather_bwd', mutates_args=())
+def rows_gather_bwd(grad_out: Tensor, idx: Tensor, num_rows: int) -> Tensor:
+    """Deterministic transpose of rows_gather: grad_x[r] = sum_{i: idx[i]==r} grad_out[i]."""
+    _need_cuda(grad_out, idx)
+    g = _rowmajor(grad_out)
+    pairs = torch.stack([idx, torch.arange(idx.numel(), device=idx.device)], dim=0)
+    rowptr, _, eid = csr_build(pairs, num_rows, True)
+    gx = torch.empty(num_rows, g.size(1), dtype=torch.float32, device=g.device)
+    L.check(lib().gnnb200_rows_gather_bwd_f32(_ptr(g), _ld(g), _ptr(rowptr), _ptr(eid), num_rows, g.size(1),
+                                             _ptr(gx), _ld(gx), _stream(g)), 'rows_gather_bwd')
+    return gx
+
+
+@rows_gather_bwd.register_fake
+def _(grad_out, idx, num_rows):
+    return grad_out.new_empty(num_rows, grad_out.size(1))
+
+
+def _rg_setup(ctx, inputs, output):
+    x, idx = inputs
+    ctx.n = x.size(0)
+    ctx.save_for_backward(idx)
+
+
+def _rg_backward(ctx, g):
+    (idx,) = ctx.saved_tensors
+    return rows_gather_bwd(g.contiguous(), idx, ctx.n), None
+
+
+rows_gather.register_autograd(_rg_backward, setup_context=_rg_setup)
+
+
+@torch.library.custom_op('gnnb200::rows_scatter', mutates_args=())
+def rows_scatter(base: Tensor, src: Tensor, idx: Tensor) -> Tensor:
+    """Copy of ``base`` with rows idx[i] replaced by src[i] (src [M,F]) or by the single row src [F]."""
+    _need_cuda(base, src, idx)
+    out = _rowmajor(base).clone()
+    broadcast = src.dim() == 1
+    s = src.contiguous().view(1, -1) if broadcast else _rowmajor(src)
+    idx = idx.contiguous()
+    L.check(lib().gnnb200_rows_scatter_f32(_ptr(s), _ld(s), int(broadcast), _ptr(idx), idx.numel(), out.size(1),
+                                          _ptr(out), _ld(out), _stream(out)), 'rows_scatter')
+    return out
+
+
+@rows_scatter.register_fake
+def _(base, src, idx):
+    return torch.empty_like(base)
+
+
+def _rs_setup(ctx, inputs, output):
+    base, src, idx = inputs
+    ctx.broadcast = src.dim() == 1
+    ctx.save_for_backward(idx)
+
+
+def _rs_backward(ctx, g):
+    (idx,) = ctx.saved_tensors
+    g = g.contiguous()
+    gsel = rows_gather(g, idx)                                     # gradient reaching the written rows
+    zero = torch.zeros(g.size(1), dtype=g.dtype, device=g.device)
+    gbase = rows_scatter(g, zero, idx)                             # overwritten rows get no gradient
+    gsrc = gsel.sum(dim=0) if ctx.broadcast else gsel
+    return gbase, gsrc, None
+
+
+rows_scatter.register_autograd(_rs_backward, setup_context=_rs_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# dense transforms
+# ---------------------------------------------------------------------------------------------
+PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_TF32}
+
+
+def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor], relu: bool,
+              precision: int) -> Tensor:
+    _need_cuda(a, b, bias)
+    a, b = _rowmajor(a), _rowmajor(b)
+    M, K = (a.size(1), a.size(0)) if transa else (a.size(0), a.size(1))
+    Kb, N = (b.size(1), b.size(0)) if transb else (b.size(0), b.size(1))
+    if K != Kb:
+        raise L.Gnnb200Error(f'gemm inner dimensions differ: {K} vs {Kb}')
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    if bias is not None:
+        bias = bias.contiguous()
+    _call_ws(lib().gnnb200_gemm_f32, 'gemm', a.device, _ptr(a), _ld(a), int(transa), _ptr(b), _ld(b), int(transb),
+             _ptr(c), _ld(c), M, N, K, _ptr(bias), L.EPI_RELU if relu else L.EPI_NONE, precision,
+             stream=_stream(a))
+    return c
+
+
+@torch.library.custom_op('gnnb200::gemm', mutates_args=())
+def gemm(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor] = None, relu: bool = False,
+         precision: int = 0) -> Tensor:
+    """C = op(a) op(b) (+bias)(ReLU), raw (no autograd): see gnnb200_gemm_f32."""
+    return _gemm_raw(a, transa, b, transb, bias, relu, precision)
+
+
+@gemm.register_fake
+def _(a, transa, b, transb, bias=None, relu=False, precision=0):
+    M = a.size(1) if transa else a.size(0)
+    N = b.size(0) if transb else b.size(1)
+    return a.new_empty(M, N)
+
+
+@torch.library.custom_op('gnnb200::colsum', mutates_args=())
+def colsum(x: Tensor) -> Tensor:
+    """Deterministic per-column sum [F] (bias gradients)."""
+    _need_cuda(x)
+    x = _rowmajor(x)
+    s = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
+    _call_ws(lib().gnnb200_colstats_f32, 'colsum', x.device, _ptr(x), _ld(x), x.size(0), x.size(1), _ptr(s), None,
+             stream=_stream(x))
+    return s
+
+
+@colsum.register_fake
+def _(x):
+    return x.new_empty(x.size(1))
+
+
+@torch.library.custom_op('gnnb200::colstats', mutates_args=())
+def colstats(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """(sum [F], centred second moment [F]) per column: BatchNorm batch statistics."""
+    _need_cuda(x)
+    x = _rowmajor(x)
+    s = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
+    m2 = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
+    _call_ws(lib().gnnb200_colstats_f32, 'colstats', x.device, _ptr(x), _ld(x), x.size(0), x.size(1), _ptr(s),
+             _ptr(m2), stream=_stream(x))
+    return s, m2
+
+
+@colstats.register_fake
+def _(x):
+    return x.new_empty(x.size(1)), x.new_empty(x.size(1))
+
+
+@torch.library.custom_op('gnnb200::linear', mutates_args=())
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int) -> Tensor:
+    """y = x W^T + b with W [out, in] (nn.Linear layout)."""
+    return _gemm_raw(x, False, weight, True, bias, False, precision)
+
+
+@linear.register_fake
+def _(x, weight, bias, precision):
+    return x.new_empty(x.size(0), weight.size(0))
+
+
+def _lin_setup(ctx, inputs, output):
+    x, weight, bias, precision = inputs
+    ctx.precision = precision
+    ctx.has_bias = bias is not None
+    ctx.save_for_backward(x, weight)
+
+
+def _lin_backward(ctx, g):
+    x, weight = ctx.saved_tensors
+    g = g.contiguous()
+    gx = gw = gb = None
+    if ctx.needs_input_grad[0]:
+        gx = gemm(g, False, weight, False, None, False, ctx.precision)      # [M,out] x [out,in]
+    if ctx.needs_input_grad[1]:
+        gw = gemm(g, True, x, False, None, False, ctx.precision)            # [out,M] x [M,in]
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        gb = colsum(g)
+    return gx, gw, gb, None
+
+
+linear.register_autograd(_lin_backward, setup_context=_lin_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# link-prediction decoder features
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('gnnb200::lp_features', mutates_args=())
+def lp_features(h: Tensor, edges: Tensor) -> Tensor:
+    """[E, 3H] = [h_u + h_v, h_u * h_v, |h_u - h_v|] for edges int64 [2, E]."""
+    _need_cuda(h, edges)
+    h = _rowmajor(h)
+    edges = edges.contiguous()
+    E, H = edges.size(1), h.size(1)
+    feat = torch.empty(E, 3 * H, dtype=torch.float32, device=h.device)
+    L.check(lib().gnnb200_lp_features_f32(_ptr(h), _ld(h), _ptr(edges), E, H, _ptr(feat), _ld(feat), _stream(h)),
+            'lp_features')
+    return feat
+
+
+@lp_features.register_fake
+def _(h, edges):
+    return h.new_empty(edges.size(1), 3 * h.size(1))
+
+
+@torch.library.custom_op('gnnb200::lp_features_bwd', mutates_args=())
+def lp_features_bwd(grad_feat: Tensor, h: Tensor, edges: Tensor) -> Tensor:
+    _need_cuda(grad_feat, h, edges)
+    g, h = _rowmajor(grad_feat), _rowmajor(h)
+    edges = edges.contiguous()
+    N, H, E = h.size(0), h.size(1), edges.size(1)
+    u_ptr, _, u_eid = csr_build(edges, N, True)
+    v_ptr, _, v_eid = csr_build(edges, N, False)
+    gh = torch.empty(N, H, dtype=torch.float32, device=h.device)
+    L.check(lib().gnnb200_lp_features_bwd_f32(
+        _ptr(h), _ld(h), _ptr(edges), E, H, _ptr(g), _ld(g), _ptr(u_ptr), _ptr(u_eid), _ptr(v_ptr), _ptr(v_eid),
+        N, _ptr(gh), _ld(gh), _stream(h)), 'lp_features_bwd')
+    return gh
+
+
+@lp_features_bwd.register_fake
+def _(grad_feat, h, edges):
+    return torch.empty_like(h)
+
+
+def _lpf_setup(ctx, inputs, output):
+    h, edges = inputs
+    ctx.save_for_backward(h, edges)
+
+
+def _lpf_backward(ctx, g):
+    h, edges = ctx.saved_tensors
+    return lp_features_bwd(g.contiguous(), h, edges), None
+
+
+lp_features.register_autograd(_lpf_backward, setup_context=_lpf_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# NT-Xent
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('gnnb200::ntxent_fwd', mutates_args=())
+def ntxent_fwd(z: Tensor, temperature: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(loss [1], zn [2M,D], lse [2M], norm [2M]) for z = cat(view1, view2) [2M, D]."""
+    _need_cuda(z)
+    z = _rowmajor(z)
+    R, D = z.size(0), z.size(1)
+    dev = z.device
+    zn = torch.empty(R, D, dtype=torch.float32, device=dev)
+    lse = torch.empty(R, dtype=torch.float32, device=dev)
+    norm = torch.empty(R, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    _call_ws(lib().gnnb200_ntxent_fwd_f32, 'ntxent_fwd', dev, _ptr(z), _ld(z), R, D, ctypes.c_float(temperature),
+             _ptr(zn), _ptr(lse), _ptr(norm), _ptr(loss), stream=_stream(z))
+    return loss, zn, lse, norm
+
+
+@ntxent_fwd.register_fake
+def _(z, temperature):
+    R = z.size(0)
+    return z.new_empty(1), torch.empty_like(z), z.new_empty(R), z.new_empty(R)
+
+
+@torch.library.custom_op('gnnb200::ntxent_bwd', mutates_args=())
+def ntxent_bwd(grad_loss: Tensor, zn: Tensor, lse: Tensor, norm: Tensor, temperature: float) -> Tensor:
+    _need_cuda(grad_loss, zn, lse, norm)
+    R, D = zn.size(0), zn.size(1)
+    gz = torch.empty(R, D, dtype=torch.float32, device=zn.device)
+    gl = grad_loss.contiguous().view(1)
+    L.check(lib().gnnb200_ntxent_bwd_f32(_ptr(zn), _ptr(lse), _ptr(norm), _ptr(gl), R, D,
+                                        ctypes.c_float(temperature), _ptr(gz), _ld(gz), _stream(zn)), 'ntxent_bwd')
+    return gz
+
+
+@ntxent_bwd.register_fake
+def _(grad_loss, zn, lse, norm, temperature):
+    return torch.empty_like(zn)
+
+
+def _ntx_setup(ctx, inputs, output):
+    z, temperature = inputs
+    loss, zn, lse, norm = output
+    ctx.temperature = temperature
+    ctx.save_for_backward(zn, lse, norm)
+
+
+def _ntx_backward(ctx, g_loss, g_zn, g_lse, g_norm):
+    zn, lse, norm = ctx.saved_tensors
+    return ntxent_bwd(g_loss.contiguous(), zn, lse, norm, ctx.temperature), None
+
+
+ntxent_fwd.register_autograd(_ntx_backward, setup_context=_ntx_setup)

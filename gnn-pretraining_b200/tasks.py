@@ -1,0 +1,269 @@
+"""Multi-task pre-training heads/losses with the reference's call surface
+(`BasePretrainTask.compute_loss(domain_batches, generator) -> (loss, per_domain)`,
+reference src/pretrain/tasks.py:61-343; called from src/pretrain/pretrain.py:124-129,220).
+Backbone passes, pooling, decoder features and the NT-Xent loss run on the gnnb200 kernels;
+loss normalisation (sum / integer count, divided once) follows the reference."""
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import ops
+from .augment import GraphAugmentor
+from .models import GRAPH_PROPERTY_DIM, PretrainableGNN
+from .nn import global_max_pool, global_mean_pool
+from .utils import batched_negative_sampling, to_undirected
+
+# reference src/pretrain/schedulers.py:3-7
+FINAL_TEMP = 0.2
+GAMMA = 10.0
+INITIAL_TEMP = 0.5
+MAX_LAMBDA = 0.01
+START_ADVERSARIAL_EPOCH_FRACTION = 0.4
+# reference src/pretrain/pretrain.py:43-52
+ACTIVE_TASKS = {
+    'b2': ['node_feat_mask'],
+    'b3': ['node_contrast'],
+    'b4': ['node_feat_mask', 'link_pred', 'node_contrast', 'graph_contrast', 'graph_prop'],
+    's1': ['node_feat_mask', 'link_pred'],
+    's2': ['node_contrast', 'graph_contrast'],
+    's3': ['node_feat_mask', 'link_pred', 'node_contrast', 'graph_contrast'],
+    's4': ['node_feat_mask', 'link_pred', 'node_contrast', 'graph_contrast', 'graph_prop'],
+    's5': ['node_feat_mask', 'link_pred', 'node_contrast', 'graph_contrast', 'graph_prop', 'domain_adv'],
+}
+
+
+class TemperatureScheduler:
+    """reference src/pretrain/schedulers.py:10-21."""
+
+    def __init__(self, total_steps: int):
+        self.total_steps = total_steps
+        self.current_step = 0
+
+    def __call__(self) -> float:
+        t = min(1.0, self.current_step / self.total_steps)
+        return float(INITIAL_TEMP * (FINAL_TEMP / INITIAL_TEMP) ** t)
+
+    def step(self):
+        self.current_step += 1
+
+
+class GRLScheduler:
+    """reference src/pretrain/schedulers.py:24-45."""
+
+    def __init__(self, total_epochs: int, steps_per_epoch: int):
+        self.total_steps = total_epochs * steps_per_epoch
+        self.start_steps = START_ADVERSARIAL_EPOCH_FRACTION * total_epochs * steps_per_epoch
+        self.current_step = 0
+
+    def __call__(self) -> float:
+        if self.current_step < self.start_steps:
+            return 0.0
+        p = float(self.current_step - self.start_steps) / float(self.total_steps - self.start_steps)
+        return float((2.0 / (1.0 + math.exp(-GAMMA * p)) - 1.0) * MAX_LAMBDA)
+
+    def step(self):
+        self.current_step += 1
+
+
+def nt_xent(z1: Tensor, z2: Tensor, temperature: float) -> Tuple[Tensor, Tensor]:
+    """reference tasks.py:192-213 / :265-287 as one fused kernel pair: normalise, tiled
+    similarity with online log-sum-exp (diagonal excluded), CE(sum) against the paired view."""
+    m = z1.size(0)
+    loss, _, _, _ = ops.ntxent_fwd(torch.cat([z1, z2], dim=0), float(temperature))
+    return loss.squeeze(0), torch.tensor(2 * m, device=z1.device, dtype=torch.long)
+
+
+def _num_graphs(batch) -> int:
+    return batch.num_graphs
+
+
+class BasePretrainTask:
+    """reference tasks.py:61-67."""
+
+    def __init__(self, model: PretrainableGNN) -> None:
+        self.model = model
+
+    def compute_loss(self, domain_batches: Dict[str, object], generator: torch.Generator
+                     ) -> Tuple[Tensor, Dict[str, Tensor]]:
+        raise NotImplementedError
+
+    def _start(self):
+        dev = self.model.device
+        return torch.tensor(0.0, device=dev), 0, {}
+
+    @staticmethod
+    def _finish(total: Tensor, count: int, always_divide: bool) -> Tensor:
+        if always_divide or count > 0:
+            total = total / count
+        return total
+
+
+class NodeFeatureMaskingTask(BasePretrainTask):
+    """reference tasks.py:70-94."""
+
+    def compute_loss(self, domain_batches, generator):
+        total, count, per_domain = self._start()
+        for name, batch in domain_batches.items():
+            masked_h0, idx, target = self.model.apply_node_masking(batch, name, generator)
+            if idx.size(0) == 0:
+                per_domain[name] = torch.tensor(0.0, device=self.model.device)
+                continue
+            h = self.model.forward_with_h0(masked_h0, batch.edge_index)
+            recon = self.model.get_head('node_feat_mask', name)(ops.rows_gather(h, idx))
+            loss = F.mse_loss(recon, target, reduction='sum')
+            size = idx.size(0) * masked_h0.size(1)
+            total = total + loss
+            count += size
+            per_domain[name] = loss / size
+        return self._finish(total, count, False), per_domain
+
+
+class LinkPredictionTask(BasePretrainTask):
+    """reference tasks.py:97-127."""
+
+    def compute_loss(self, domain_batches, generator):
+        dev = self.model.device
+        total, count, per_domain = self._start()
+        decoder = self.model.get_head('link_pred')
+        for name, batch in domain_batches.items():
+            pos = batch.edge_index
+            neg = batched_negative_sampling(edge_index=to_undirected(pos), batch=batch.batch,
+                                            num_neg_samples=pos.size(1))
+            edges = torch.cat([pos, neg], dim=1)
+            labels = torch.cat([torch.ones(pos.size(1), device=dev), torch.zeros(neg.size(1), device=dev)])
+            probs = decoder(self.model(batch, name), edges)
+            loss = F.binary_cross_entropy(probs, labels, reduction='sum')
+            size = labels.size(0)
+            total = total + loss
+            count += size
+            per_domain[name] = loss / size
+        return self._finish(total, count, True), per_domain
+
+
+class NodeContrastiveTask(BasePretrainTask):
+    """reference tasks.py:130-213.  The per-graph boolean-mask loop of :153-164 becomes one index
+    vector per view (same rows, same order) and a single row-gather kernel."""
+
+    def __init__(self, model, temperature_scheduler: TemperatureScheduler):
+        super().__init__(model)
+        self.temperature_scheduler = temperature_scheduler
+
+    @staticmethod
+    def _common_rows(view, masks) -> Tensor:
+        starts = view.ptr.tolist()
+        rows = [torch.nonzero(m, as_tuple=False).view(-1) + starts[g] for g, m in enumerate(masks)]
+        return torch.cat(rows) if rows else torch.empty(0, dtype=torch.long, device=view.x.device)
+
+    def compute_loss(self, domain_batches, generator):
+        dev = self.model.device
+        total, count, per_domain = self._start()
+        temperature = self.temperature_scheduler()
+        for name, batch in domain_batches.items():
+            v1, v2, m1, m2 = GraphAugmentor.create_two_views(batch, generator)
+            h1 = self.model(v1, name)
+            h2 = self.model(v2, name)
+            r1, r2 = self._common_rows(v1, m1), self._common_rows(v2, m2)
+            if r1.numel() < 2 or r2.numel() < 2:
+                per_domain[name] = torch.tensor(0.0, device=dev)
+                continue
+            proj = self.model.get_head('node_contrast', name)
+            z1 = proj(ops.rows_gather(h1, r1.to(dev)))
+            z2 = proj(ops.rows_gather(h2, r2.to(dev)))
+            loss, size = self._simclr_nt_xent(z1, z2, temperature)
+            total = total + loss
+            count += int(2 * z1.size(0))
+            per_domain[name] = loss / size
+        return self._finish(total, count, False), per_domain
+
+    def _simclr_nt_xent(self, z1, z2, temperature):
+        return nt_xent(z1, z2, temperature)
+
+
+class GraphContrastiveTask(BasePretrainTask):
+    """reference tasks.py:216-287."""
+
+    def __init__(self, model, temperature_scheduler: TemperatureScheduler = None):
+        super().__init__(model)
+        self.temperature_scheduler = temperature_scheduler
+
+    def compute_loss(self, domain_batches, generator):
+        dev = self.model.device
+        total, count, per_domain = self._start()
+        temperature = self.temperature_scheduler()
+        for name, batch in domain_batches.items():
+            if _num_graphs(batch) < 2:
+                per_domain[name] = torch.tensor(0.0, device=dev)
+                continue
+            v1, v2, _, _ = GraphAugmentor.create_two_views(batch, generator)
+            s = []
+            for view in (v1, v2):
+                h = self.model(view, name)
+                b = _num_graphs(view)
+                s.append(torch.cat([global_mean_pool(h, view.batch, b), global_max_pool(h, view.batch, b)], dim=1))
+            proj = self.model.get_head('graph_contrast', name)
+            loss, size = self._graph_contrastive_loss(proj(s[0]), proj(s[1]), temperature)
+            total = total + loss
+            count += int(2 * s[0].size(0))
+            per_domain[name] = loss / size
+        return self._finish(total, count, False), per_domain
+
+    def _graph_contrastive_loss(self, z1, z2, temperature):
+        return nt_xent(z1, z2, temperature)
+
+
+class GraphPropertyPredictionTask(BasePretrainTask):
+    """reference tasks.py:290-312."""
+
+    def compute_loss(self, domain_batches, generator):
+        dev = self.model.device
+        total, count, per_domain = self._start()
+        for name, batch in domain_batches.items():
+            emb = global_mean_pool(self.model(batch, name), batch.batch, _num_graphs(batch))
+            pred = self.model.get_head('graph_prop', name)(emb)
+            labels = batch.graph_properties.to(torch.float32).to(dev).view(emb.size(0), GRAPH_PROPERTY_DIM)
+            loss = F.mse_loss(pred, labels, reduction='sum')
+            size = emb.size(0) * GRAPH_PROPERTY_DIM
+            total = total + loss
+            count += size
+            per_domain[name] = loss / size
+        return self._finish(total, count, True), per_domain
+
+
+class DomainAdversarialTask(BasePretrainTask):
+    """reference tasks.py:315-343."""
+
+    def __init__(self, model: PretrainableGNN, grl_scheduler: GRLScheduler = None) -> None:
+        super().__init__(model)
+        self.domain_to_idx = {n: i for i, n in enumerate(self.model.input_encoders.keys())}
+        self.grl_scheduler = grl_scheduler
+
+    def compute_loss(self, domain_batches, generator):
+        dev = self.model.device
+        total, count, per_domain = self._start()
+        lam = self.grl_scheduler() if self.grl_scheduler is not None else 0.0
+        for name, batch in domain_batches.items():
+            emb = global_mean_pool(self.model(batch, name), batch.batch, _num_graphs(batch))
+            logits = self.model.get_head('domain_adv')(emb, lam)
+            labels = torch.full((emb.size(0),), self.domain_to_idx[name], device=dev, dtype=torch.long)
+            loss = F.cross_entropy(logits, labels, reduction='sum')
+            size = labels.size(0)
+            total = total + loss
+            count += size
+            per_domain[name] = loss / size
+        return self._finish(total, count, True), per_domain
+
+
+def instantiate_tasks(model, active_tasks, grl_scheduler, temperature_scheduler):
+    """reference src/pretrain/pretrain.py:77-93."""
+    make = {
+        'node_feat_mask': lambda: NodeFeatureMaskingTask(model),
+        'link_pred': lambda: LinkPredictionTask(model),
+        'node_contrast': lambda: NodeContrastiveTask(model, temperature_scheduler),
+        'graph_contrast': lambda: GraphContrastiveTask(model, temperature_scheduler),
+        'graph_prop': lambda: GraphPropertyPredictionTask(model),
+        'domain_adv': lambda: DomainAdversarialTask(model, grl_scheduler),
+    }
+    return {t: make[t]() for t in active_tasks if t in make}

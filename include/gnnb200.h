@@ -1,0 +1,177 @@
+/* gnnb200.h — C ABI of libgnnb200.so: the B200 (sm_100a) message-passing hot path.
+ *
+ * The reference (alonbebchuk/GNN-Pretraining) has no FFI: its seam is the Python nn.Module /
+ * function surface over PyTorch-Geometric.  Each entry point below names the reference call
+ * site (paths relative to the reference root) or the PyG primitive whose
+ * device work it replaces.  The Python binding a maintainer adds is in INTEGRATION.md.
+ *
+ * Conventions (all functions):
+ *   - plain pointers to DEVICE memory, sizes as int64_t, no torch types;
+ *   - returns 0 on success, a negative GNNB200_E* code, or a positive cudaError_t;
+ *   - never allocates, never synchronises, no mutable global state: re-entrant across streams;
+ *   - scratch is caller-provided: calling with workspace == NULL writes the required size to
+ *     *workspace_bytes and returns 0 without launching anything;
+ *   - row-major matrices with an explicit leading dimension in ELEMENTS;
+ *   - reductions have a fixed order: same inputs -> same bits, no float atomics anywhere.
+ */
+#ifndef GNNB200_H_
+#define GNNB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* gnnb200_stream_t; /* == cudaStream_t */
+
+#define GNNB200_OK 0
+#define GNNB200_EINVAL (-1)     /* bad argument (null pointer, negative size, bad mode)      */
+#define GNNB200_ERANGE (-2)     /* N or E does not fit the int32 CSR (>= 2^31)               */
+#define GNNB200_EWORKSPACE (-3) /* workspace too small                                        */
+#define GNNB200_EUNSUPPORTED (-4) /* shape/alignment not supported by this kernel              */
+
+int gnnb200_version(void);
+const char* gnnb200_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * CSR / CSC build.  Replaces the COO gather + scatter_add indexing of PyG GINConv.propagate
+ * (src/models/gnn.py:41; SURVEY §8a note): bit-exact with
+ *     perm   = torch.sort(key_row, stable=True).indices      -> eid
+ *     col    = other_row[perm]
+ *     rowptr = cat([0, cumsum(bincount(key_row, minlength=N))])
+ * edge_index is [2, E] int64 row-major (row 0 = src, row 1 = dst).  by_src = 0 groups by dst
+ * (forward aggregation), by_src = 1 groups by src (transposed graph, backward pass).
+ * eid may be NULL.  Indices must lie in [0, N).
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_csr_build_i64(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                          int by_src, int32_t* rowptr, int32_t* col, int32_t* eid,
+                          void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+
+/* Segment offsets of a SORTED int64 id vector (PyG Batch.batch -> ptr, App. A.6):
+ * ptr[g] = first position with ids[pos] >= g, ptr[num_segments] = n. */
+int gnnb200_segment_ptr_i64(const int64_t* ids, int64_t n, int64_t num_segments, int32_t* ptr,
+                            gnnb200_stream_t stream);
+
+/* to_undirected()'s coalesce (src/pretrain/tasks.py:108; App. A.4): sort the E columns by
+ * row*N+col ascending and drop duplicates.  out is [2, E] (capacity), *out_count (device)
+ * receives the number of kept columns; unused tail columns are left untouched. */
+int gnnb200_coalesce_i64(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                         int64_t* out, int64_t* out_count, void* workspace, size_t* workspace_bytes,
+                         gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-destination aggregation over a CSR (K1/K2/K1^T of SURVEY §2.4; GINConv of
+ * src/models/gnn.py:29-37,41; modes of App. A.7):
+ *   SUM : out[i] = sum_{e in row i} x[col[e]]                       (edge order, from 0.0f)
+ *   MEAN: out[i] = SUM / max(deg_i, 1)
+ *   GCN : out[i] = sum_e (dinv[col[e]]*dinv[i]) * x[col[e]] + (dinv[i]*dinv[i]) * x_self[i]
+ * and, when self_x != NULL (SUM/MEAN): out[i] += (1 + *eps) * self_x[i]   (eps NULL -> 0).
+ * The backward pass is the same call on the by_src CSR with x = grad (transposed gather).
+ * feat is the row width; x/self_x/out have leading dimensions ldx/lds/ldo (elements).
+ * ------------------------------------------------------------------------------------------ */
+#define GNNB200_AGG_SUM 0
+#define GNNB200_AGG_MEAN 1
+#define GNNB200_AGG_GCN 2
+int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
+                          int64_t num_rows, int64_t feat, int mode, const float* self_x, int64_t lds,
+                          const float* eps, const float* dinv, float* out, int64_t ldo,
+                          gnnb200_stream_t stream);
+
+/* Deterministic dot product sum(a*b) over n elements -> *out (device).  d(eps) of GINConv. */
+int gnnb200_dot_f32(const float* a, const float* b, int64_t n, float* out, void* workspace,
+                    size_t* workspace_bytes, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Global graph pooling over contiguous segments (global_mean_pool / global_max_pool,
+ * src/models/finetune_model.py:75, src/pretrain/tasks.py:241-246,299,331; App. A.2/A.3).
+ * ptr is int32 [num_segments+1].  Empty segments give 0 rows.
+ *   fwd: out [num_segments, feat]
+ *   bwd: MEAN/SUM dx[r] = g[seg(r)] (/ max(cnt,1));  MAX follows torch's native amax rule:
+ *        dx[r,c] = g[s,c] * [x[r,c]==out[s,c]] / (ties + (out[s,c]==0 ? 1 : 0)).
+ * ------------------------------------------------------------------------------------------ */
+#define GNNB200_POOL_SUM 0
+#define GNNB200_POOL_MEAN 1
+#define GNNB200_POOL_MAX 2
+int gnnb200_segment_pool_fwd_f32(const float* x, int64_t ldx, const int32_t* ptr, int64_t num_rows,
+                                 int64_t num_segments, int64_t feat, int mode, float* out, int64_t ldo,
+                                 void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+int gnnb200_segment_pool_bwd_f32(const float* grad_out, int64_t ldg, const float* x, int64_t ldx,
+                                 const float* out, int64_t ldo, const int32_t* ptr, int64_t num_rows,
+                                 int64_t num_segments, int64_t feat, int mode, float* grad_x, int64_t ldgx,
+                                 gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row gather / scatter (K12: NFM mask-token write and target gather,
+ * src/models/pretrain_model.py:84-86; h[mask_indices] at src/pretrain/tasks.py:82).
+ *   gather : out[i]      = x[idx[i]]
+ *   scatter: out[idx[i]] = src[i]  (or the single broadcast row src when broadcast != 0)
+ *   gather_bwd: grad_x[r] = sum of grad_out rows i with idx[i] == r, in ascending i (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_rows_gather_f32(const float* x, int64_t ldx, const int64_t* idx, int64_t num_idx,
+                            int64_t feat, float* out, int64_t ldo, gnnb200_stream_t stream);
+int gnnb200_rows_scatter_f32(const float* src, int64_t lds, int broadcast, const int64_t* idx,
+                             int64_t num_idx, int64_t feat, float* out, int64_t ldo,
+                             gnnb200_stream_t stream);
+/* rowptr/eid: CSR over idx built by gnnb200_csr_build_i64 on [idx; arange] with by_src = 1
+ * (rows = x rows, eid = positions in grad_out, ascending). */
+int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_t* rowptr,
+                                const int32_t* eid, int64_t num_rows, int64_t feat, float* grad_x,
+                                int64_t ldgx, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense transforms (K3: nn.Linear of src/models/gnn.py:13,31,34 and src/models/heads.py:41).
+ *   C[M,N] = op(A) * op(B) (+ bias[N]) (ReLU)        op = identity or transpose
+ *   A is [M,K] (transa=0) or [K,M] (transa=1); B is [K,N] (transb=0) or [N,K] (transb=1).
+ * precision: F32 = fp32 FFMA (1e-5 class); TF32 = tcgen05.mma kind::tf32 with TMA-fed
+ * shared-memory tiles and TMEM fp32 accumulators (2e-2 class).  TF32 needs a TMA-legal
+ * layout (16-byte aligned bases, ld % 4 == 0); otherwise GNNB200_EUNSUPPORTED.
+ * ------------------------------------------------------------------------------------------ */
+#define GNNB200_GEMM_F32 0
+#define GNNB200_GEMM_TF32 1
+#define GNNB200_EPI_NONE 0
+#define GNNB200_EPI_RELU 1
+int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
+                     float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
+                     int epilogue, int precision, void* workspace, size_t* workspace_bytes,
+                     gnnb200_stream_t stream);
+
+/* Column statistics over rows (K4 BatchNorm1d batch stats of src/models/gnn.py:15,32,38 and bias
+ * gradients): sum[c] = sum_r x[r,c]; when sumsq != NULL also the centred second moment
+ * m2[c] = sum_r (x[r,c]-mean_c)^2 (Chan merge of per-block Welford partials). */
+int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* sum,
+                         float* m2, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Link-prediction decoder input (K8, src/models/heads.py:59-65): for each edge (u,v)
+ *   feat[e] = [h[u]+h[v], h[u]*h[v], |h[u]-h[v]|]   -> [E, 3*H]
+ * and its backward into grad_h (deterministic: edges grouped per node by the caller's CSRs).
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_lp_features_f32(const float* h, int64_t ldh, const int64_t* edges, int64_t num_edges,
+                            int64_t hidden, float* feat, int64_t ldf, gnnb200_stream_t stream);
+/* u_ptr/u_eid: CSR of the edge list grouped by edges[0] (by_src = 1), v_ptr/v_eid grouped by edges[1]
+ * (by_src = 0), both from gnnb200_csr_build_i64 with eid requested. */
+int gnnb200_lp_features_bwd_f32(const float* h, int64_t ldh, const int64_t* edges, int64_t num_edges,
+                                int64_t hidden, const float* grad_feat, int64_t ldf, const int32_t* u_ptr,
+                                const int32_t* u_eid, const int32_t* v_ptr, const int32_t* v_eid,
+                                int64_t num_nodes, float* grad_h, int64_t ldgh, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NT-Xent / InfoNCE (K9, src/pretrain/tasks.py:192-213,265-287): z is [2M, D] (already the
+ * concatenation of both views, NOT yet normalised).  Computes row-normalised z, the row-wise
+ * log-sum-exp of z z^T / T with the diagonal excluded, and loss = sum_i (lse_i - sim_{i,pos(i)}).
+ * Never materialises the [2M,2M] matrix.  fwd writes loss (1 float), lse [2M], norm [2M] (= ||z_i||) and
+ * zn [2M,D] (dense); bwd writes grad_z [2M,D] given d(loss) (1 float, device).  bwd: D % 16 == 0, D <= 128.
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_ntxent_fwd_f32(const float* z, int64_t ldz, int64_t two_m, int64_t dim, float temperature,
+                           float* zn, float* lse, float* norm, float* loss, void* workspace,
+                           size_t* workspace_bytes, gnnb200_stream_t stream);
+int gnnb200_ntxent_bwd_f32(const float* zn, const float* lse, const float* norm, const float* grad_loss,
+                           int64_t two_m, int64_t dim, float temperature, float* grad_z, int64_t ldgz,
+                           gnnb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNB200_H_ */
