@@ -119,7 +119,7 @@ extern "C" int gnnb200_csr_build_i64(const int64_t* edge_index, int64_t E, int64
     return GNNB200_OK;
   }
   if (*workspace_bytes < ws.bytes()) return GNNB200_EWORKSPACE;
-  if (!edge_index || !rowptr || (!col && E > 0)) return GNNB200_EINVAL;
+  if (!rowptr || (E > 0 && (!edge_index || !col))) return GNNB200_EINVAL;
   const int64_t* key_row = edge_index + (by_src ? 0 : E);
   const int64_t* other_row = edge_index + (by_src ? E : 0);
   if (E > 0) {

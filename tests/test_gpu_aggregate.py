@@ -1,0 +1,113 @@
+"""Neighbour aggregation fwd/bwd against the oracle (CPU scatter_add_ in edge order): bit-exact
+for the sum / (1+eps) self term / transposed backward; 1e-5 for the eps gradient (tree reduce)."""
+import pytest
+import torch
+
+import gnnb200  # noqa: F401
+from gnnb200 import _lib as L
+from gnnb200 import ops, synthetic
+from gnnb200.graph import Graph
+from gnnb200.nn import GINConv
+from oracle import install_pyg_shim
+
+install_pyg_shim()
+from torch_geometric.nn import GINConv as OracleGINConv  # noqa: E402
+from torch_geometric.utils import scatter  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (2, e), generator=g)
+
+
+@pytest.mark.parametrize('n,e,f', [(1, 0, 256), (10, 0, 256), (64, 300, 256), (2708, 10556, 256), (500, 4000, 512),
+                                   (300, 2000, 128), (300, 2000, 64), (300, 2000, 16), (300, 2000, 100),
+                                   (300, 2000, 21), (200, 1500, 7), (100, 900, 1028), (50, 5000, 256)])
+def test_gin_aggregate_forward_bit_exact(n, e, f):
+    ei = _graph(n, e, n + e + f)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    eps = torch.tensor([0.37])
+    want = scatter(x.index_select(0, ei[0]), ei[1], dim=0, dim_size=n, reduce='sum') + (1 + eps) * x
+    gr = Graph(ei.to(DEV), n)
+    got = ops.gin_aggregate(x.to(DEV), eps.to(DEV), gr.rowptr, gr.col, gr.rowptr.new_empty(0), gr.col.new_empty(0))
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize('n,e,f', [(64, 300, 256), (2708, 10556, 256), (300, 2000, 100), (200, 1500, 7)])
+def test_gin_aggregate_backward(n, e, f):
+    ei = _graph(n, e, 3 * n + e)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(2))
+    gout = torch.randn(n, f, generator=torch.Generator().manual_seed(3))
+    xo = x.clone().requires_grad_(True)
+    eo = torch.tensor([0.21], requires_grad=True)
+    zo = scatter(xo.index_select(0, ei[0]), ei[1], dim=0, dim_size=n, reduce='sum') + (1 + eo) * xo
+    zo.backward(gout)
+    gr = Graph(ei.to(DEV), n)
+    xg = x.to(DEV).requires_grad_(True)
+    eg = torch.tensor([0.21], device=DEV, requires_grad=True)
+    z = ops.gin_aggregate(xg, eg, gr.rowptr, gr.col, gr.rowptr_t, gr.col_t)
+    z.backward(gout.to(DEV))
+    assert torch.equal(z.detach().cpu(), zo.detach())
+    assert torch.equal(xg.grad.cpu(), xo.grad)                      # a+b == b+a: still bit-exact
+    torch.testing.assert_close(eg.grad.cpu(), eo.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_ginconv_module_matches_oracle_module():
+    n, e, h = 500, 3000, 256
+    ei = _graph(n, e, 9)
+    x = torch.randn(n, h, generator=torch.Generator().manual_seed(4))
+    mk = lambda lin: torch.nn.Sequential(lin(h, 2 * h), torch.nn.ReLU(), lin(2 * h, h))
+    from gnnb200.nn import Linear
+    a = OracleGINConv(mk(torch.nn.Linear), train_eps=True)
+    b = GINConv(mk(Linear), train_eps=True)
+    b.load_state_dict(a.state_dict())
+    b = b.to(DEV)
+    ya = a(x, ei)
+    yb = b(x.to(DEV), ei.to(DEV))
+    assert float((ya - yb.cpu()).abs().max() / ya.abs().max()) < 1e-5    # fp32 class
+
+
+@pytest.mark.parametrize('f', [256, 100, 30])
+def test_mean_and_gcn_modes_formula_oracle(f):
+    """Extra modes requested by the north star (not used by the reference): SURVEY.md App. A.7."""
+    n, e = 400, 3000
+    ei = _graph(n, e, 77)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(5))
+    gr = Graph(ei.to(DEV), n)
+    want_mean = scatter(x.index_select(0, ei[0]), ei[1], dim=0, dim_size=n, reduce='mean')
+    got_mean = ops.aggregate(x.to(DEV), gr.rowptr, gr.col, L.AGG_MEAN)
+    assert torch.equal(got_mean.cpu(), want_mean)
+    # GCN symmetric norm with self loops appended after the existing edges
+    deg = torch.bincount(ei[1], minlength=n).float() + 1.0
+    dinv = deg.pow(-0.5)
+    src = torch.cat([ei[0], torch.arange(n)])
+    dst = torch.cat([ei[1], torch.arange(n)])
+    w = dinv[src] * dinv[dst]
+    want_gcn = scatter(w.view(-1, 1) * x.index_select(0, src), dst, dim=0, dim_size=n, reduce='sum')
+    got_gcn = ops.aggregate(x.to(DEV), gr.rowptr, gr.col, L.AGG_GCN, x.to(DEV), None, dinv.to(DEV))
+    assert torch.equal(got_gcn.cpu(), want_gcn)
+
+
+def test_large_graph_properties():
+    """Size-independent checks at a scale the CPU oracle would take long on: linearity in x and the
+    all-ones identity (row sums = in-degree + 1 + eps)."""
+    n, e, f = 200_000, 5_000_000, 256
+    d = synthetic.products_like(n, e, 8, seed=1, device=DEV)
+    gr = Graph(d['edge_index'], n)
+    eps = torch.tensor([0.5], device=DEV)
+    empty = gr.rowptr.new_empty(0)
+    ones = torch.ones(n, f, device=DEV)
+    z = ops.gin_aggregate(ones, eps, gr.rowptr, gr.col, empty, empty)
+    want = (gr.in_degree().float() + 1.5).view(-1, 1).expand(n, f)
+    assert torch.equal(z, want)
+    a = torch.randn(n, f, device=DEV)
+    b = torch.randn(n, f, device=DEV)
+    za = ops.gin_aggregate(a, eps, gr.rowptr, gr.col, empty, empty)
+    zb = ops.gin_aggregate(b, eps, gr.rowptr, gr.col, empty, empty)
+    zab = ops.gin_aggregate(a + b, eps, gr.rowptr, gr.col, empty, empty)
+    assert float((zab - (za + zb)).abs().max()) < 1e-3 * float(zab.abs().max())
+    # determinism: same bits on a second run
+    assert torch.equal(za, ops.gin_aggregate(a, eps, gr.rowptr, gr.col, empty, empty))

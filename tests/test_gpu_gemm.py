@@ -1,0 +1,70 @@
+"""Dense transforms: fp32 FFMA path within 1e-5 (relative to the output scale) of torch fp32 on the
+CPU; all operand layouts, ragged sizes, split-K, bias/ReLU epilogues, and nn.Linear autograd."""
+import pytest
+import torch
+
+import gnnb200  # noqa: F401
+from gnnb200 import ops
+from gnnb200.nn import Linear
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL_F32 = 1e-5      # north_star: 1e-5 relative for fp32 paths
+TOL_TF32 = 2e-2     # north_star: 2e-2 for reduced-precision GEMM paths
+
+
+def _rel(got, want):
+    return float((got.double().cpu() - want.double()).abs().max() / want.double().abs().max().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize('m,n,k', [(1, 1, 1), (5, 3, 2), (64, 64, 16), (130, 70, 33), (2708, 256, 1433), (4100, 512, 256),
+                                   (300, 256, 512), (17, 1, 256), (512, 256, 20000)])
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_f32_layouts(m, n, k, ta, tb):
+    g = torch.Generator().manual_seed(m * 7 + n * 3 + k)
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    want = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    got = ops.gemm(a.to(DEV), ta, b.to(DEV), tb, None, False, 0)
+    assert got.shape == (m, n)
+    assert _rel(got, want) < TOL_F32
+
+
+def test_gemm_bias_relu_epilogue_and_strided_input():
+    g = torch.Generator().manual_seed(0)
+    big = torch.randn(300, 600, generator=g)
+    a = big[:, 100:356]                       # leading dimension 600, unit inner stride
+    w = torch.randn(512, 256, generator=g)
+    bias = torch.randn(512, generator=g)
+    want = torch.relu(a.double() @ w.double().t() + bias.double())
+    got = ops.gemm(big.to(DEV)[:, 100:356], False, w.to(DEV), True, bias.to(DEV), True, 0)
+    assert _rel(got, want) < TOL_F32
+
+
+@pytest.mark.parametrize('rows,fin,fout', [(4096, 256, 512), (333, 21, 256), (2708, 1433, 256), (128, 768, 1)])
+def test_linear_autograd(rows, fin, fout):
+    g = torch.Generator().manual_seed(rows)
+    ref = torch.nn.Linear(fin, fout)
+    lin = Linear(fin, fout)
+    lin.load_state_dict(ref.state_dict())
+    lin = lin.to(DEV)
+    x = torch.randn(rows, fin, generator=g)
+    go = torch.randn(rows, fout, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).backward(go)
+    xg = x.to(DEV).requires_grad_(True)
+    y = lin(xg)
+    y.backward(go.to(DEV))
+    assert _rel(y, ref(x).detach()) < TOL_F32
+    assert _rel(xg.grad, xr.grad) < TOL_F32
+    assert _rel(lin.weight.grad, ref.weight.grad) < 2e-5
+    assert _rel(lin.bias.grad, ref.bias.grad) < 2e-5
+
+
+def test_colstats_match_batchnorm_statistics():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5000, 512, generator=g) * 3 + 50.0      # large mean: catches cancellation
+    s, m2 = ops.colstats(x.to(DEV))
+    assert _rel(s / 5000, x.double().mean(0)) < 1e-6
+    assert _rel(m2 / 5000, x.double().var(0, unbiased=False)) < 1e-5
+    assert torch.equal(ops.colsum(x.to(DEV)), s)          # same kernel, same bits

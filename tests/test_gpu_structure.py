@@ -1,0 +1,78 @@
+"""CSR build / segment ptr / coalesce: bit-exact against the torch expressions the contract is
+defined by (SURVEY.md §8a note) and the oracle's coalesce."""
+import pytest
+import torch
+
+import gnnb200  # noqa: F401
+from gnnb200 import ops, synthetic, utils
+from oracle import install_pyg_shim
+
+install_pyg_shim()
+from torch_geometric import utils as oracle_utils  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _ref_csr(ei, n, by_src):
+    key, other = (ei[0], ei[1]) if by_src else (ei[1], ei[0])
+    perm = torch.sort(key, stable=True).indices
+    deg = torch.bincount(key, minlength=n)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)])
+    return rowptr, other[perm], perm
+
+
+@pytest.mark.parametrize('n,e', [(1, 0), (5, 0), (7, 1), (100, 1000), (2708, 10556), (4097, 50001), (300000, 1000003)])
+@pytest.mark.parametrize('by_src', [False, True])
+def test_csr_build_bit_exact(n, e, by_src):
+    g = torch.Generator().manual_seed(n * 31 + e)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    rowptr, col, eid = ops.csr_build(ei.to(DEV), n, by_src)
+    r_ref, c_ref, p_ref = _ref_csr(ei, n, by_src)
+    assert rowptr.dtype == torch.int32 and col.dtype == torch.int32
+    assert torch.equal(rowptr.cpu().long(), r_ref)
+    assert torch.equal(col.cpu().long(), c_ref)
+    assert torch.equal(eid.cpu().long(), p_ref)
+
+
+def test_csr_build_skewed_and_isolated_rows():
+    n = 1000
+    ei = torch.stack([torch.randint(0, n, (5000,)), torch.cat([torch.full((4000,), 17), torch.randint(900, n, (1000,))])])
+    rowptr, col, _ = ops.csr_build(ei.to(DEV), n, False)
+    r_ref, c_ref, _ = _ref_csr(ei, n, False)
+    assert torch.equal(rowptr.cpu().long(), r_ref) and torch.equal(col.cpu().long(), c_ref)
+
+
+def test_degrees_match_bincount():
+    from gnnb200.graph import Graph
+    d = synthetic.cora_like()
+    gr = Graph(d['edge_index'].to(DEV), d['x'].size(0))
+    assert torch.equal(gr.in_degree().cpu(), torch.bincount(d['edge_index'][1], minlength=d['x'].size(0)))
+    assert torch.equal(gr.out_degree().cpu(), torch.bincount(d['edge_index'][0], minlength=d['x'].size(0)))
+
+
+@pytest.mark.parametrize('sizes', [[3], [0, 4, 0, 0, 2], [5, 1, 7, 126, 2], [1] * 300])
+def test_segment_ptr(sizes):
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    ptr = ops.segment_ptr(batch.to(DEV), len(sizes))
+    ref = torch.cat([torch.zeros(1, dtype=torch.long), torch.tensor(sizes).cumsum(0)])
+    assert torch.equal(ptr.cpu().long(), ref)
+
+
+@pytest.mark.parametrize('n,e', [(4, 3), (50, 400), (2708, 10556), (100000, 400000)])
+def test_to_undirected_matches_oracle(n, e):
+    g = torch.Generator().manual_seed(e)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    got = utils.to_undirected(ei.to(DEV), num_nodes=n).cpu()
+    want = oracle_utils.to_undirected(ei, num_nodes=n)
+    assert torch.equal(got, want)
+    # idempotent + sorted + unique (size-independent properties)
+    again = utils.to_undirected(got.to(DEV), num_nodes=n).cpu()
+    assert torch.equal(again, got)
+    key = got[0] * n + got[1]
+    assert bool((key[1:] > key[:-1]).all())
+
+
+def test_coalesce_infers_num_nodes_like_upstream():
+    ei = torch.tensor([[0, 3, 3, 1], [3, 0, 0, 2]])
+    assert torch.equal(utils.to_undirected(ei.to(DEV)).cpu(), oracle_utils.to_undirected(ei))
