@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the gnnb200 hot path (contract: see the task statement).
+
+Workload (config.workload = "c5_products_backbone"): BASELINE.json configs[4], the largest config
+and the one the metric's "% HBM roofline" is quoted on — a synthetic ogbn-products-shaped graph
+(N=2,449,029 nodes, E=61,859,140 directed edges in arbitrary COO order, F_in=100, hidden 256),
+InputEncoder + 5-layer GIN backbone in TRAIN mode (BatchNorm batch statistics, dropout active),
+loss = h.sum(), backward, AdamW step.  One step = CSR+CSC build from edge_index, forward,
+backward, optimizer.  metric = aggregated edges/sec = E * L * 2 (fwd + bwd sweeps) / step time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S] [--locality P]
+
+N > 1 (launched by torch.distributed.run): the same graph node-partitioned into N contiguous
+destination ranges with an NCCL all-gather of the layer input per layer ("strong" scaling).
+--impl reference times the reference's CPU path (the oracle: reference modules restated over the
+PyG shim) on a bounded node/edge sample of the same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'aggregated_edges_per_sec_fwd_bwd'
+UNIT = 'edges/s'
+LAYERS = 5
+HIDDEN = 256
+C5_N, C5_E, C5_F = 2_449_029, 61_859_140, 100
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': float(p['hbm_gbs']), 'source': 'measured (MEASURED_PEAKS.json, burst copy)'}
+    return {'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def aggregation_bytes(n, e, f):
+    """Algorithmic bytes of one aggregation pass: neighbour rows (no-reuse gather
+    model) + self-term read + output write + col ids + row pointers."""
+    return e * f * 4 + n * f * 4 + n * f * 4 + e * 4 + (n + 1) * 4
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index=0, period=0.2):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for attr, label in (('nvmlClocksEventReasonHwSlowdown', 'hw_slowdown'),
+                            ('nvmlClocksEventReasonHwThermalSlowdown', 'hw_thermal_slowdown'),
+                            ('nvmlClocksEventReasonSwThermalSlowdown', 'sw_thermal_slowdown'),
+                            ('nvmlClocksEventReasonSwPowerCap', 'sw_power_cap'),
+                            ('nvmlClocksThrottleReasonHwSlowdown', 'hw_slowdown'),
+                            ('nvmlClocksThrottleReasonHwThermalSlowdown', 'hw_thermal_slowdown'),
+                            ('nvmlClocksThrottleReasonSwThermalSlowdown', 'sw_thermal_slowdown'),
+                            ('nvmlClocksThrottleReasonSwPowerCap', 'sw_power_cap')):
+            if hasattr(nv, attr):
+                names[getattr(nv, attr)] = label
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                    getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+                mask = get(self.h)
+                for bit, label in names.items():
+                    if mask & bit:
+                        self.reasons.add(label)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        return {'sm_mhz': statistics.median(self.samples) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_graph(n, e, f, seed, locality, device):
+    from gnnb200 import synthetic
+    return synthetic.products_like(n, e, f, seed=seed, locality=locality, device=device)
+
+
+def build_model(impl_models, device, f_in, seed=0):
+    torch.manual_seed(seed)
+    enc = impl_models.InputEncoder(f_in, HIDDEN)
+    bb = impl_models.GINBackbone(LAYERS, HIDDEN)
+    model = torch.nn.ModuleDict({'input_encoder': enc, 'gnn_backbone': bb}).to(device)
+    model.train()
+    return model
+
+
+def step_fn(model, opt, x, edge_index):
+    """One training step of the hot path.  `edge_index.view_as` gives a fresh tensor object, so the
+    CSR/CSC build is part of every step (no cached structure carried across steps)."""
+    ei = edge_index.view_as(edge_index)
+    opt.zero_grad(set_to_none=True)
+    h = model['gnn_backbone'](model['input_encoder'](x), ei)
+    loss = h.sum()
+    loss.backward()
+    opt.step()
+    return loss
+
+
+def run_product(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import gnnb200  # noqa: F401
+    from gnnb200 import models as prod, ops
+    from gnnb200 import nn as gnn
+    if args.precision:
+        gnn.set_default_precision(args.precision)
+
+    n = max(1024, int(C5_N * args.scale))
+    e = max(4096, int(C5_E * args.scale))
+    data = make_graph(n, e, C5_F, 42, args.locality, dev)
+    x_dev, ei_dev = data['x'], data['edge_index']
+
+    if world > 1:
+        from gnnb200 import partition
+        runner = partition.PartitionedBackboneStep(prod, dev, C5_F, HIDDEN, LAYERS, n, rank, world)
+        one_step = lambda x, ei: runner.step(x, ei)  # noqa: E731
+    else:
+        model = build_model(prod, dev, C5_F)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        one_step = lambda x, ei: step_fn(model, opt, x, ei)  # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        one_step(x_dev, ei_dev)
+    barrier()
+    ops.reset_counters()
+    ops.AGG_TIMER = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            one_step(x_dev, ei_dev)
+        stop.record()
+        barrier()
+    ms = start.elapsed_time(stop)
+    agg_ms = [a.elapsed_time(b) for a, b in ops.AGG_TIMER]
+    ops.AGG_TIMER = None
+    launches = ops.launch_count()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_per_step = ms / args.steps
+    value = e * LAYERS * 2 / (ms_per_step / 1e3)
+
+    # ---- end-to-end leg: host buffers, H2D of the step's inputs and D2H of the loss every step ----
+    x_host = x_dev.cpu().pin_memory()
+    ei_host = ei_dev.cpu().pin_memory()
+    del x_dev, ei_dev, data
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        eid = ei_host.to(dev, non_blocking=True)
+        loss = one_step(xd, eid)
+        return float(loss.detach().cpu())          # D2H read of the step's result
+
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.no_e2e:
+        s2.record()
+        e2.record()
+        barrier()
+    else:
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        s2.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e2.record()
+        barrier()
+    t2 = torch.tensor([max(s2.elapsed_time(e2), 1e-9)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2) / args.steps
+    e2e_value = e * LAYERS * 2 / (e2e_ms / 1e3)
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        n_local = (n + world - 1) // world
+        e_local = e // world
+        agg_bytes = aggregation_bytes(n_local, e_local, HIDDEN)
+        agg_avg = statistics.mean(agg_ms) if agg_ms else None
+        achieved = agg_bytes / (agg_avg / 1e3) / 1e9 if agg_avg else None
+        traffic = None
+        prof = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if os.path.isfile(prof):
+            traffic = json.load(open(prof)).get(f'aggregate_scale{args.scale}_loc{args.locality}')
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32' if gnn.default_precision() == 'f32' else 'f32+tf32',
+            'data': 'synthetic',
+            'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F,
+                       'hidden': HIDDEN, 'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
+                       'edge_locality': args.locality, 'gemm_precision': gnn.default_precision(),
+                       'l2_policy': 'inputs_larger_than_L2 (2.5 GB activations per layer vs 126 MB L2)',
+                       'parallelism': 'single' if world == 1 else f'node_partition{world}+halo_allgather'},
+            'clocks': clocks.summary(),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4},
+            'gpu_launches': launches,
+            'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30,
+            'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM> (fwd and transposed bwd)',
+                         'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': achieved / pk['hbm_gbs'] if achieved else None, 'traffic': traffic,
+                         'peak_source': pk['source'], 'launches_timed': len(agg_ms),
+                         'avg_launch_ms': agg_avg, 'algorithmic_bytes_per_launch': agg_bytes,
+                         'share_of_step': (sum(agg_ms) / ms) if agg_ms else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline(args, budget_steps=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the oracle = the reference's modules restated over the pure-PyTorch PyG shim)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_sizes(args):
+    frac = args.cpu_sample
+    return max(1024, int(C5_N * args.scale * frac)), max(4096, int(C5_E * args.scale * frac))
+
+
+def cpu_run(args, steps, warmup):
+    from oracle import modules as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, e = cpu_sample_sizes(args)
+    data = make_graph(n, e, C5_F, 42, args.locality, 'cpu')
+    model = build_model(orc, torch.device('cpu'), C5_F)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step_fn(model, opt, data['x'], data['edge_index'])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n, e, sec
+
+
+def cpu_baseline(args, budget_steps=1):
+    n, e, sec = cpu_run(args, steps=budget_steps, warmup=1)
+    return {'value': e * LAYERS * 2 / sec, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{n} nodes / {e} edges ({args.cpu_sample:g} of the workload), same model, '
+                      f'{budget_steps} timed step(s) of {sec:.2f} s after 1 warm-up', 'seconds_per_step': sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return None
+    n, e, sec = cpu_run(args, steps=args.steps, warmup=args.warmup)
+    value = e * LAYERS * 2 / sec
+    base = {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{n} nodes / {e} edges ({args.cpu_sample:g} of the workload) per step'}
+    return {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F, 'hidden': HIDDEN,
+                   'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW on host cores (oracle port of the reference)',
+                   'edge_locality': args.locality},
+        'cpu_baseline': base,
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='gnnb200', choices=['gnnb200', 'reference'])
+    ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C5 graph (debug only; 1.0 = BASELINE config)')
+    ap.add_argument('--locality', type=float, default=0.0, help='fraction of intra-block edges (0 = uniform random)')
+    ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32'])
+    ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        out = run_reference(args)
+    else:
+        out = run_product(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()

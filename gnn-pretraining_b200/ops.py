@@ -56,12 +56,46 @@ def _ld(t: Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
 
 
-def _call_ws(fn, what: str, device, *args, stream: int):
+# Own-kernel launches per entry-point call (library kernels such as CUB's sort are not counted).
+KERNELS_PER_CALL = {
+    'gnnb200_csr_build_i64': 2, 'gnnb200_segment_ptr_i64': 1, 'gnnb200_coalesce_i64': 3,
+    'gnnb200_aggregate_f32': 1, 'gnnb200_dot_f32': 2, 'gnnb200_segment_pool_fwd_f32': 1,
+    'gnnb200_segment_pool_bwd_f32': 1, 'gnnb200_rows_gather_f32': 1, 'gnnb200_rows_scatter_f32': 1,
+    'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_colstats_f32': 2,
+    'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
+    'gnnb200_ntxent_bwd_f32': 1,
+}
+_calls = {}
+AGG_TIMER = None      # bench.py sets this to a list to collect (start, stop) CUDA events per aggregation launch
+
+
+def reset_counters() -> None:
+    _calls.clear()
+
+
+def call_counts() -> dict:
+    return dict(_calls)
+
+
+def launch_count() -> int:
+    """Kernels of this library launched since reset_counters() (lower bound: split-K finish passes
+    and chunked-pool finish passes are not added)."""
+    return sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in _calls.items())
+
+
+def _invoke(name: str, *args) -> int:
+    _calls[name] = _calls.get(name, 0) + 1
+    return getattr(lib(), name)(*args)
+
+
+def _call_ws(name: str, what: str, device, *args, stream: int):
     """Two-phase call of an entry point whose trailing args are (workspace, &bytes, stream)."""
+    fn = getattr(lib(), name)
     need = c_size_t(0)
     L.check(fn(*args, None, byref(need), stream), what + ' (workspace query)')
     ws = torch.empty(max(int(need.value), 256), dtype=torch.uint8, device=device)
     have = c_size_t(ws.numel())
+    _calls[name] = _calls.get(name, 0) + 1
     L.check(fn(*args, ws.data_ptr(), byref(have), stream), what)
     return ws
 
@@ -81,7 +115,7 @@ def csr_build(edge_index: Tensor, num_nodes: int, by_src: bool) -> Tuple[Tensor,
     rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
     col = torch.empty(E, dtype=torch.int32, device=dev)
     eid = torch.empty(E, dtype=torch.int32, device=dev)
-    _call_ws(lib().gnnb200_csr_build_i64, 'csr_build', dev, _ptr(ei), E, num_nodes, int(by_src),
+    _call_ws('gnnb200_csr_build_i64', 'csr_build', dev, _ptr(ei), E, num_nodes, int(by_src),
              _ptr(rowptr), _ptr(col), _ptr(eid), stream=_stream(ei))
     return rowptr, col, eid
 
@@ -99,7 +133,7 @@ def segment_ptr(ids: Tensor, num_segments: int) -> Tensor:
     _need_cuda(ids)
     ids = ids.contiguous()
     out = torch.empty(num_segments + 1, dtype=torch.int32, device=ids.device)
-    L.check(lib().gnnb200_segment_ptr_i64(_ptr(ids), ids.numel(), num_segments, _ptr(out), _stream(ids)),
+    L.check(_invoke('gnnb200_segment_ptr_i64', _ptr(ids), ids.numel(), num_segments, _ptr(out), _stream(ids)),
             'segment_ptr')
     return out
 
@@ -117,7 +151,7 @@ def coalesce(edge_index: Tensor, num_nodes: int) -> Tuple[Tensor, Tensor]:
     E = ei.size(1)
     out = torch.empty_like(ei)
     count = torch.zeros(1, dtype=torch.int64, device=ei.device)
-    _call_ws(lib().gnnb200_coalesce_i64, 'coalesce', ei.device, _ptr(ei), E, num_nodes, _ptr(out), _ptr(count),
+    _call_ws('gnnb200_coalesce_i64', 'coalesce', ei.device, _ptr(ei), E, num_nodes, _ptr(out), _ptr(count),
              stream=_stream(ei))
     return out, count
 
@@ -138,10 +172,17 @@ def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Op
     out = torch.empty(n_rows, x.size(1), dtype=torch.float32, device=x.device)
     if self_x is not None:
         self_x = _rowmajor(self_x)
-    L.check(lib().gnnb200_aggregate_f32(
+    timer = AGG_TIMER
+    if timer is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    L.check(_invoke('gnnb200_aggregate_f32',
         _ptr(x), _ld(x), _ptr(rowptr), _ptr(col), n_rows, x.size(1), mode,
         _ptr(self_x), _ld(self_x) if self_x is not None else 0, _ptr(eps), _ptr(dinv),
         _ptr(out), _ld(out), _stream(x)), 'aggregate')
+    if timer is not None:
+        ev[1].record()
+        timer.append(ev)
     return out
 
 
@@ -163,7 +204,7 @@ def dot(a: Tensor, b: Tensor) -> Tensor:
     _need_cuda(a, b)
     a, b = a.contiguous(), b.contiguous()
     out = torch.empty(1, dtype=torch.float32, device=a.device)
-    _call_ws(lib().gnnb200_dot_f32, 'dot', a.device, _ptr(a), _ptr(b), a.numel(), _ptr(out), stream=_stream(a))
+    _call_ws('gnnb200_dot_f32', 'dot', a.device, _ptr(a), _ptr(b), a.numel(), _ptr(out), stream=_stream(a))
     return out
 
 
@@ -215,7 +256,7 @@ def segment_pool(x: Tensor, ptr: Tensor, mode: int) -> Tensor:
     x = _rowmajor(x)
     S = ptr.numel() - 1
     out = torch.empty(S, x.size(1), dtype=torch.float32, device=x.device)
-    _call_ws(lib().gnnb200_segment_pool_fwd_f32, 'segment_pool', x.device, _ptr(x), _ld(x), _ptr(ptr), x.size(0), S,
+    _call_ws('gnnb200_segment_pool_fwd_f32', 'segment_pool', x.device, _ptr(x), _ld(x), _ptr(ptr), x.size(0), S,
              x.size(1), mode, _ptr(out), _ld(out), stream=_stream(x))
     return out
 
@@ -231,7 +272,7 @@ def segment_pool_bwd(grad_out: Tensor, x: Tensor, out: Tensor, ptr: Tensor, mode
     g, x, out = _rowmajor(grad_out), _rowmajor(x), _rowmajor(out)
     S = ptr.numel() - 1
     gx = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
-    L.check(lib().gnnb200_segment_pool_bwd_f32(
+    L.check(_invoke('gnnb200_segment_pool_bwd_f32', 
         _ptr(g), _ld(g), _ptr(x), _ld(x), _ptr(out), _ld(out), _ptr(ptr), x.size(0), S, x.size(1), mode,
         _ptr(gx), _ld(gx), _stream(x)), 'segment_pool_bwd')
     return gx
@@ -266,7 +307,7 @@ def rows_gather(x: Tensor, idx: Tensor) -> Tensor:
     x = _rowmajor(x)
     idx = idx.contiguous()
     out = torch.empty(idx.numel(), x.size(1), dtype=torch.float32, device=x.device)
-    L.check(lib().gnnb200_rows_gather_f32(_ptr(x), _ld(x), _ptr(idx), idx.numel(), x.size(1), _ptr(out), _ld(out),
+    L.check(_invoke('gnnb200_rows_gather_f32', _ptr(x), _ld(x), _ptr(idx), idx.numel(), x.size(1), _ptr(out), _ld(out),
                                          _stream(x)), 'rows_gather')
     return out
 
@@ -284,7 +325,7 @@ def rows_gather_bwd(grad_out: Tensor, idx: Tensor, num_rows: int) -> Tensor:
     pairs = torch.stack([idx, torch.arange(idx.numel(), device=idx.device)], dim=0)
     rowptr, _, eid = csr_build(pairs, num_rows, True)
     gx = torch.empty(num_rows, g.size(1), dtype=torch.float32, device=g.device)
-    L.check(lib().gnnb200_rows_gather_bwd_f32(_ptr(g), _ld(g), _ptr(rowptr), _ptr(eid), num_rows, g.size(1),
+    L.check(_invoke('gnnb200_rows_gather_bwd_f32', _ptr(g), _ld(g), _ptr(rowptr), _ptr(eid), num_rows, g.size(1),
                                              _ptr(gx), _ld(gx), _stream(g)), 'rows_gather_bwd')
     return gx
 
@@ -316,7 +357,7 @@ def rows_scatter(base: Tensor, src: Tensor, idx: Tensor) -> Tensor:
     broadcast = src.dim() == 1
     s = src.contiguous().view(1, -1) if broadcast else _rowmajor(src)
     idx = idx.contiguous()
-    L.check(lib().gnnb200_rows_scatter_f32(_ptr(s), _ld(s), int(broadcast), _ptr(idx), idx.numel(), out.size(1),
+    L.check(_invoke('gnnb200_rows_scatter_f32', _ptr(s), _ld(s), int(broadcast), _ptr(idx), idx.numel(), out.size(1),
                                           _ptr(out), _ld(out), _stream(out)), 'rows_scatter')
     return out
 
@@ -362,7 +403,7 @@ def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[T
     c = torch.empty(M, N, dtype=torch.float32, device=a.device)
     if bias is not None:
         bias = bias.contiguous()
-    _call_ws(lib().gnnb200_gemm_f32, 'gemm', a.device, _ptr(a), _ld(a), int(transa), _ptr(b), _ld(b), int(transb),
+    _call_ws('gnnb200_gemm_f32', 'gemm', a.device, _ptr(a), _ld(a), int(transa), _ptr(b), _ld(b), int(transb),
              _ptr(c), _ld(c), M, N, K, _ptr(bias), L.EPI_RELU if relu else L.EPI_NONE, precision,
              stream=_stream(a))
     return c
@@ -388,7 +429,7 @@ def colsum(x: Tensor) -> Tensor:
     _need_cuda(x)
     x = _rowmajor(x)
     s = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
-    _call_ws(lib().gnnb200_colstats_f32, 'colsum', x.device, _ptr(x), _ld(x), x.size(0), x.size(1), _ptr(s), None,
+    _call_ws('gnnb200_colstats_f32', 'colsum', x.device, _ptr(x), _ld(x), x.size(0), x.size(1), _ptr(s), None,
              stream=_stream(x))
     return s
 
@@ -405,7 +446,7 @@ def colstats(x: Tensor) -> Tuple[Tensor, Tensor]:
     x = _rowmajor(x)
     s = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
     m2 = torch.empty(x.size(1), dtype=torch.float32, device=x.device)
-    _call_ws(lib().gnnb200_colstats_f32, 'colstats', x.device, _ptr(x), _ld(x), x.size(0), x.size(1), _ptr(s),
+    _call_ws('gnnb200_colstats_f32', 'colstats', x.device, _ptr(x), _ld(x), x.size(0), x.size(1), _ptr(s),
              _ptr(m2), stream=_stream(x))
     return s, m2
 
@@ -460,7 +501,7 @@ def lp_features(h: Tensor, edges: Tensor) -> Tensor:
     edges = edges.contiguous()
     E, H = edges.size(1), h.size(1)
     feat = torch.empty(E, 3 * H, dtype=torch.float32, device=h.device)
-    L.check(lib().gnnb200_lp_features_f32(_ptr(h), _ld(h), _ptr(edges), E, H, _ptr(feat), _ld(feat), _stream(h)),
+    L.check(_invoke('gnnb200_lp_features_f32', _ptr(h), _ld(h), _ptr(edges), E, H, _ptr(feat), _ld(feat), _stream(h)),
             'lp_features')
     return feat
 
@@ -479,7 +520,7 @@ def lp_features_bwd(grad_feat: Tensor, h: Tensor, edges: Tensor) -> Tensor:
     u_ptr, _, u_eid = csr_build(edges, N, True)
     v_ptr, _, v_eid = csr_build(edges, N, False)
     gh = torch.empty(N, H, dtype=torch.float32, device=h.device)
-    L.check(lib().gnnb200_lp_features_bwd_f32(
+    L.check(_invoke('gnnb200_lp_features_bwd_f32', 
         _ptr(h), _ld(h), _ptr(edges), E, H, _ptr(g), _ld(g), _ptr(u_ptr), _ptr(u_eid), _ptr(v_ptr), _ptr(v_eid),
         N, _ptr(gh), _ld(gh), _stream(h)), 'lp_features_bwd')
     return gh
@@ -517,7 +558,7 @@ def ntxent_fwd(z: Tensor, temperature: float) -> Tuple[Tensor, Tensor, Tensor, T
     lse = torch.empty(R, dtype=torch.float32, device=dev)
     norm = torch.empty(R, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    _call_ws(lib().gnnb200_ntxent_fwd_f32, 'ntxent_fwd', dev, _ptr(z), _ld(z), R, D, ctypes.c_float(temperature),
+    _call_ws('gnnb200_ntxent_fwd_f32', 'ntxent_fwd', dev, _ptr(z), _ld(z), R, D, ctypes.c_float(temperature),
              _ptr(zn), _ptr(lse), _ptr(norm), _ptr(loss), stream=_stream(z))
     return loss, zn, lse, norm
 
@@ -534,7 +575,7 @@ def ntxent_bwd(grad_loss: Tensor, zn: Tensor, lse: Tensor, norm: Tensor, tempera
     R, D = zn.size(0), zn.size(1)
     gz = torch.empty(R, D, dtype=torch.float32, device=zn.device)
     gl = grad_loss.contiguous().view(1)
-    L.check(lib().gnnb200_ntxent_bwd_f32(_ptr(zn), _ptr(lse), _ptr(norm), _ptr(gl), R, D,
+    L.check(_invoke('gnnb200_ntxent_bwd_f32', _ptr(zn), _ptr(lse), _ptr(norm), _ptr(gl), R, D,
                                         ctypes.c_float(temperature), _ptr(gz), _ld(gz), _stream(zn)), 'ntxent_bwd')
     return gz
 
