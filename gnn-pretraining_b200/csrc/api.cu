@@ -36,8 +36,14 @@ extern "C" int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const f
   if (precision == GNNB200_GEMM_F32)
     return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, epilogue, workspace,
                               workspace_bytes, stream);
-  if (precision == GNNB200_GEMM_TF32) {
-    if (!gnnb200::gemm_tf32_supported(A, lda, transa, B, ldb, transb, C, ldc, M, N, K)) return GNNB200_EUNSUPPORTED;
+  if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_AUTO) {
+    // the support predicate only reads sizes, leading dimensions and pointer alignment; during the
+    // workspace query C may be NULL (NULL is 16-byte aligned), so both phases take the same branch
+    if (!gnnb200::gemm_tf32_supported(A, lda, transa, B, ldb, transb, C, ldc, M, N, K)) {
+      if (precision == GNNB200_GEMM_TF32) return GNNB200_EUNSUPPORTED;
+      return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, epilogue, workspace,
+                                workspace_bytes, stream);
+    }
     return gnnb200::gemm_tf32(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, epilogue, workspace,
                               workspace_bytes, stream);
   }

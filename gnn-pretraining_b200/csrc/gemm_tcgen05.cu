@@ -1,8 +1,473 @@
-// placeholder until the tcgen05 kernel lands (next commit): reports "unsupported" for every shape.
+// TF32 tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with TMA-fed 128B-swizzled shared
+// memory tiles and fp32 accumulators in TMEM.  Replaces the cuBLAS addmm calls behind nn.Linear
+// forward/backward in the reference (src/models/gnn.py:13,31,34; src/models/heads.py:41), K3 of
+// SURVEY §2.4.  fp32 operands are consumed in place (kind::tf32 reads 32-bit words from shared
+// memory), so no cast pass is needed.
+//
+//   C[M,N] = op(A) op(B) (+bias)(ReLU),  op(A) is [M,K], op(B) is [K,N]
+//   A "K-major"  : stored [M,K] row-major (transa=0)      A "MN-major": stored [K,M] (transa=1)
+//   B "K-major"  : stored [N,K] row-major (transb=1)      B "MN-major": stored [K,N] (transb=0)
+//
+// Persistent kernel, one CTA per SM, 256 threads:
+//   warp 0   TMA producer (one elected lane): kStages-deep ring of {A tile 128x32, B tile BNx32} fp32
+//   warp 1   MMA issuer  (one elected lane): 4 x tcgen05.mma (M=128, N=BN, K=8) per stage,
+//            tcgen05.commit releases the stage; accumulators double-buffered in TMEM (2 x BN columns)
+//   warp 2   TMEM allocator (512 columns)
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/ReLU -> 128-bit global stores,
+//            overlapped with the next tile's main loop
+// Split-K (used for the weight gradients, K = number of nodes): each (tile, split) writes an fp32
+// partial to the workspace, a second kernel sums the splits in order (deterministic) and applies the
+// epilogue.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the store.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace gnnb200 {
-int gemm_tf32_supported(const float*, int64_t, int, const float*, int64_t, int, const float*, int64_t, int64_t,
-                        int64_t, int64_t) { return 0; }
-int gemm_tf32(const float*, int64_t, int, const float*, int64_t, int, float*, int64_t, int64_t, int64_t, int64_t,
-              const float*, int, void*, size_t*, cudaStream_t) { return GNNB200_EUNSUPPORTED; }
+
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M (cta_group::1)
+constexpr int BK = 32;           // fp32 elements per stage along K = one 128-byte swizzle span
+constexpr int UMMA_K = 8;        // kind::tf32
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kSpinLimit = 1u << 27;   // bounded mbarrier spin: trap instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (SM100 UMMA): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64): 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B
+// (the only legal layout for MN-major 32-bit operands: 128 B rows, 32 B swizzle atoms, 4-row groups).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// Instruction descriptor: D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2, a_major bit15, b_major bit16,
+// N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Params {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, k_blocks_per_split;
+  float* C;          // output, or the split-K partial buffer [splits][M][N]
+  long long ldc;
+  const float* bias;  // applied only when splits == 1
+  int relu;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
+  constexpr uint32_t kBBytes = BN * BK * 4;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kSlabBytes = BK * 128;   // MN-major: one 32-wide slab = BK rows x 128 B
+  constexpr uint32_t kIdesc = make_idesc(BN, A_MN, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kb0, int& kb1, int& split) {
+    const int nt = t % p.n_tiles;
+    const int rest = t / p.n_tiles;
+    const int mt = rest % p.m_tiles;
+    split = rest / p.m_tiles;
+    m0 = mt * BM;
+    n0 = nt * BN;
+    kb0 = split * p.k_blocks_per_split;
+    kb1 = min(k_blocks_total, kb0 + p.k_blocks_per_split);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb0, kb1, split;
+        tile_coords(t, m0, n0, kb0, kb1, split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int s = 0; s < BM / 32; ++s) tma_load_2d(&map_a, &full_bar[stage], sa + s * kSlabBytes, m0 + 32 * s, k0);
+          } else {
+            tma_load_2d(&map_a, &full_bar[stage], sa, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int s = 0; s < BN / 32; ++s) tma_load_2d(&map_b, &full_bar[stage], sb + s * kSlabBytes, n0 + 32 * s, k0);
+          } else {
+            tma_load_2d(&map_b, &full_bar[stage], sb, k0, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb0, kb1, split;
+        tile_coords(t, m0, n0, kb0, kb1, split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA (K=8 tf32) advances 32 B inside
+            // the swizzle span.  MN-major: 32-wide slabs kSlabBytes apart (LBO), 4-row groups 512 B apart
+            // (SBO); one MMA consumes 8 k-rows = 1024 B.
+            const uint64_t da = A_MN ? make_desc(sa + k * 1024, kSlabBytes, 512, kLayoutSw128Base32)
+                                     : make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+            const uint64_t db = B_MN ? make_desc(sb + k * 1024, kSlabBytes, 512, kLayoutSw128Base32)
+                                     : make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
+            umma_tf32(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);              // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7 <-> TMEM lanes 0..127) =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m0, n0, kb0, kb1, split;
+      tile_coords(t, m0, n0, kb0, kb1, split);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + q * 32 + lane;
+      float* crow = p.C + (p.splits > 1 ? (long long)split * p.M * p.N : 0) + (long long)row * p.ldc + n0;
+      const bool has_k = kb1 > kb0;                    // an empty split contributes zeros
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = n0 + c * 32 + j;
+            if (col < p.N) {                            // N % 4 == 0 is guaranteed by the host
+              float4 o;
+              o.x = has_k ? __uint_as_float(v[j + 0]) : 0.f;
+              o.y = has_k ? __uint_as_float(v[j + 1]) : 0.f;
+              o.z = has_k ? __uint_as_float(v[j + 2]) : 0.f;
+              o.w = has_k ? __uint_as_float(v[j + 3]) : 0.f;
+              if (p.splits == 1) {
+                if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if (p.relu) {
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+              }
+              *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long mn, int N, const float* __restrict__ bias,
+                     int relu, float* __restrict__ C, long long ldc) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= mn) return;
+  float4 acc = *reinterpret_cast<const float4*>(partial + i4);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + (long long)s * mn + i4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const long long m = i4 / N;
+  const int n = (int)(i4 % N);
+  if (bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+  *reinterpret_cast<float4*>(C + m * ldc + n) = acc;
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;   // benign race: every thread resolves the same pointer
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch ld elements,
+// box {32 floats = 128 B, box_outer rows}, zero fill out of bounds; 128-byte swizzle with 16 B atoms for
+// K-major tiles and with 32 B atoms for MN-major tiles (matches the UMMA descriptor layout types).
+static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_outer,
+                    bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return GNNB200_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GNNB200_OK : GNNB200_EUNSUPPORTED;
+}
+
+static int pick_bn(long long N) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  if (N >= 256) return 256;   // ragged last tile: TMA zero-fills, the store masks (N % 4 == 0 required)
+  if (N >= 128) return 128;
+  return 64;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kStages * (BM * BK * 4 + BN * BK * 4) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, kThreads, smem, stream>>>(ma, mb, p);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+template <int BN>
+static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid,
+                     cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, p, grid, stream);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, p, grid, stream);
+  if (a_mn && !b_mn) return launch<BN, true, false>(ma, mb, p, grid, stream);
+  return launch<BN, true, true>(ma, mb, p, grid, stream);
+}
+
+}  // namespace tc
+
+int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
+                        const float* C, int64_t ldc, int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (N % 4 != 0 || N < 8) return 0;
+  if (lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0) return 0;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return 0;
+  if (M >= (1LL << 31) || K >= (1LL << 31)) return 0;
+  (void)transa; (void)transb;
+  return tc::encode_fn() != nullptr;
+}
+
+int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
+              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int epilogue, void* workspace,
+              size_t* workspace_bytes, cudaStream_t stream) {
+  using namespace tc;
+  const int bn = pick_bn(N);
+  const int m_tiles = (int)((M + BM - 1) / BM);
+  const int n_tiles = (int)((N + bn - 1) / bn);
+  const int k_blocks = (int)((K + BK - 1) / BK);
+  // split-K only when the output has too few tiles to fill the machine and K is long
+  int splits = 1;
+  const long long tiles = (long long)m_tiles * n_tiles;
+  if (tiles * 2 <= kNumSMs && k_blocks >= 64) {
+    splits = (int)(kNumSMs / tiles);
+    const int max_s = k_blocks / 16;
+    if (splits > max_s) splits = max_s;
+    if (splits < 1) splits = 1;
+  }
+  const int kbps = (k_blocks + splits - 1) / splits;
+  splits = (k_blocks + kbps - 1) / kbps;
+  Workspace ws(workspace);
+  float* partial = splits > 1 ? ws.take<float>((size_t)splits * M * N) : nullptr;
+  if (!workspace) {
+    *workspace_bytes = ws.bytes();
+    return GNNB200_OK;
+  }
+  if (*workspace_bytes < ws.bytes()) return GNNB200_EWORKSPACE;
+
+  const bool a_mn = transa != 0;   // stored [K,M]
+  const bool b_mn = transb == 0;   // stored [K,N]
+  CUtensorMap ma, mb;
+  int rc;
+  if (a_mn) rc = make_map(&ma, A, M, K, lda, BK, true);            // inner = M, outer = K, box {32, BK}
+  else rc = make_map(&ma, A, K, M, lda, BM, false);                 // inner = K, outer = M, box {32, 128}
+  if (rc) return rc;
+  if (b_mn) rc = make_map(&mb, B, N, K, ldb, BK, true);
+  else rc = make_map(&mb, B, K, N, ldb, bn, false);
+  if (rc) return rc;
+
+  Params p;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits; p.k_blocks_per_split = kbps;
+  p.C = splits > 1 ? partial : C;
+  p.ldc = splits > 1 ? N : ldc;
+  p.bias = splits > 1 ? nullptr : bias;
+  p.relu = (splits == 1 && (epilogue & GNNB200_EPI_RELU)) ? 1 : 0;
+  const long long total = tiles * splits;
+  const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+  if (bn == 256) rc = launch_bn<256>(a_mn, b_mn, ma, mb, p, grid, stream);
+  else if (bn == 128) rc = launch_bn<128>(a_mn, b_mn, ma, mb, p, grid, stream);
+  else rc = launch_bn<64>(a_mn, b_mn, ma, mb, p, grid, stream);
+  if (rc) return rc;
+  if (splits > 1) {
+    const long long mn = (long long)M * N;
+    splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, stream>>>(partial, splits, mn, (int)N, bias,
+                                                                               (epilogue & GNNB200_EPI_RELU) ? 1 : 0, C, ldc);
+    GNNB200_LAUNCH_CHECK();
+  }
+  return GNNB200_OK;
+}
+
 }  // namespace gnnb200

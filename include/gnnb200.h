@@ -130,6 +130,7 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
  * ------------------------------------------------------------------------------------------ */
 #define GNNB200_GEMM_F32 0
 #define GNNB200_GEMM_TF32 1
+#define GNNB200_GEMM_AUTO 2 /* TF32 tensor path when the layout allows it, else the fp32 FFMA kernel */
 #define GNNB200_EPI_NONE 0
 #define GNNB200_EPI_RELU 1
 int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,

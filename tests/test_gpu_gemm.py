@@ -68,3 +68,75 @@ def test_colstats_match_batchnorm_statistics():
     assert _rel(s / 5000, x.double().mean(0)) < 1e-6
     assert _rel(m2 / 5000, x.double().var(0, unbiased=False)) < 1e-5
     assert torch.equal(ops.colsum(x.to(DEV)), s)          # same kernel, same bits
+
+
+# ---- tcgen05 / TMEM / TMA path (kind::tf32): the 2e-2 tolerance class ---------------------------------
+@pytest.mark.parametrize('m,n,k', [(128, 256, 32), (128, 256, 256), (256, 512, 256), (4100, 512, 256), (4100, 256, 512),
+                                   (333, 256, 100), (5000, 128, 64), (1000, 64, 96), (777, 100, 256), (129, 8, 40),
+                                   (20000, 256, 256), (1, 256, 256)])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tf32_tensor_core_path(m, n, k, ta, tb):
+    g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
+    if (ta and m % 4) or (not ta and k % 4) or (tb and k % 4) or (not tb and n % 4):
+        pytest.skip('TMA needs 16-byte row pitches')
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    bias = torch.randn(n, generator=g)
+    want = (a.t() if ta else a).double() @ (b.t() if tb else b).double() + bias.double()
+    got = ops.gemm(a.to(DEV), ta, b.to(DEV), tb, bias.to(DEV), False, ops.PRECISIONS['tf32_strict'])
+    err = _rel(got, want)
+    assert err < TOL_TF32, err
+    assert err < 5e-3, err          # tf32 (10-bit mantissa) with fp32 accumulate is far inside the class
+
+
+def test_gemm_tf32_split_k_weight_gradient_shape():
+    """dW = dY^T X with K = number of nodes: both operands MN-major, split-K, deterministic."""
+    g = torch.Generator().manual_seed(1)
+    dy = torch.randn(60000, 512, generator=g)
+    x = torch.randn(60000, 256, generator=g)
+    want = dy.double().t() @ x.double()
+    got1 = ops.gemm(dy.to(DEV), True, x.to(DEV), False, None, False, ops.PRECISIONS['tf32_strict'])
+    got2 = ops.gemm(dy.to(DEV), True, x.to(DEV), False, None, False, ops.PRECISIONS['tf32_strict'])
+    assert torch.equal(got1, got2)
+    assert _rel(got1, want) < 5e-3
+
+
+def test_gemm_tf32_relu_epilogue_and_exact_small_integers():
+    """Small integers are exact in tf32: any layout / swizzle / descriptor mistake shows up as a wrong
+    integer, not as rounding noise."""
+    g = torch.Generator().manual_seed(2)
+    a = torch.randint(-4, 5, (640, 256), generator=g).float()
+    w = torch.randint(-4, 5, (512, 256), generator=g).float()
+    bias = torch.randint(-4, 5, (512,), generator=g).float()
+    want = torch.relu(a @ w.t() + bias)
+    got = ops.gemm(a.to(DEV), False, w.to(DEV), True, bias.to(DEV), True, ops.PRECISIONS['tf32_strict'])
+    assert torch.equal(got.cpu(), want)
+
+
+def test_linear_autograd_tf32():
+    g = torch.Generator().manual_seed(4)
+    ref = torch.nn.Linear(256, 512)
+    lin = Linear(256, 512)
+    lin.precision = 'tf32'
+    lin.load_state_dict(ref.state_dict())
+    lin = lin.to(DEV)
+    x = torch.randn(9000, 256, generator=g)
+    go = torch.randn(9000, 512, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).backward(go)
+    xg = x.to(DEV).requires_grad_(True)
+    y = lin(xg)
+    y.backward(go.to(DEV))
+    assert _rel(y, ref(x).detach()) < 5e-3
+    assert _rel(xg.grad, xr.grad) < 5e-3
+    assert _rel(lin.weight.grad, ref.weight.grad) < 5e-3
+    assert _rel(lin.bias.grad, ref.bias.grad) < 1e-5
+
+
+def test_tf32_falls_back_to_ffma_only_for_illegal_layouts():
+    a = torch.randn(50, 1433, device=DEV)      # row pitch 1433 floats: not 16-byte aligned
+    w = torch.randn(256, 1433, device=DEV)
+    with pytest.raises(Exception):
+        ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32_strict'])
+    got = ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32'])
+    assert _rel(got, a.double().cpu() @ w.double().cpu().t()) < TOL_F32
