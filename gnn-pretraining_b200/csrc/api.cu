@@ -21,6 +21,7 @@ extern "C" const char* gnnb200_error_string(int code) {
     case GNNB200_ERANGE: return "size does not fit the int32 CSR / grid limits";
     case GNNB200_EWORKSPACE: return "workspace too small";
     case GNNB200_EUNSUPPORTED: return "shape or alignment not supported by this kernel";
+    case GNNB200_ETMA: return "TMA tensor-map encode failed";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown gnnb200 error";
   }
 }

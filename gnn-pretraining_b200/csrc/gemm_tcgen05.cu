@@ -19,6 +19,7 @@
 // partial to the workspace, a second kernel sums the splits in order (deterministic) and applies the
 // epilogue.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the store.
 #include <cuda.h>
+#include <stdio.h>
 #include "common.cuh"
 
 namespace gnnb200 {
@@ -353,7 +354,15 @@ static EncodeTiledFn encode_fn() {
 static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_outer,
                     bool mn_major) {
   EncodeTiledFn fn = encode_fn();
-  if (!fn) return GNNB200_EUNSUPPORTED;
+  if (!fn) return GNNB200_ETMA;
+  // The driver entry point needs a current context on THIS host thread.  Threads that have only been
+  // handed a device ordinal (e.g. PyTorch's autograd worker) may not have the primary context bound
+  // yet; a no-op runtime call binds it.
+  static thread_local bool context_bound = false;
+  if (!context_bound) {
+    cudaFree(nullptr);
+    context_bound = true;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
@@ -363,7 +372,12 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? GNNB200_OK : GNNB200_EUNSUPPORTED;
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "gnnb200: cuTensorMapEncodeTiled failed (CUresult %d): base=%p inner=%lld outer=%lld ld=%lld box_outer=%d mn=%d\n",
+            (int)r, (const void*)base, inner, outer, ld, box_outer, (int)mn_major);
+    return GNNB200_ETMA;
+  }
+  return GNNB200_OK;
 }
 
 static int pick_bn(long long N) {

@@ -31,6 +31,7 @@ typedef struct CUstream_st* gnnb200_stream_t; /* == cudaStream_t */
 #define GNNB200_ERANGE (-2)     /* N or E does not fit the int32 CSR (>= 2^31)               */
 #define GNNB200_EWORKSPACE (-3) /* workspace too small                                        */
 #define GNNB200_EUNSUPPORTED (-4) /* shape/alignment not supported by this kernel              */
+#define GNNB200_ETMA (-5)       /* TMA tensor-map encode failed (driver entry point / arguments) */
 
 int gnnb200_version(void);
 const char* gnnb200_error_string(int code);
