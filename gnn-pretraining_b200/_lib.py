@@ -4,7 +4,7 @@ There is no CPU or eager fallback: if the shared library is missing, loading fai
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgnnb200.so')
@@ -33,8 +33,11 @@ SIGNATURES = {
     'gnnb200_rows_gather_f32': [P, I64, P, I64, I64, P, I64, P],
     'gnnb200_rows_scatter_f32': [P, I64, c_int, P, I64, I64, P, I64, P],
     'gnnb200_rows_gather_bwd_f32': [P, I64, P, P, I64, I64, P, I64, P],
-    'gnnb200_gemm_f32': [P, I64, c_int, P, I64, c_int, P, I64, I64, I64, I64, P, c_int, c_int, P, SZP, P],
+    'gnnb200_gemm_f32': [P, I64, c_int, P, I64, c_int, P, I64, I64, I64, I64, P, P, I64, c_int, c_int, P, SZP, P],
     'gnnb200_colstats_f32': [P, I64, I64, I64, P, P, P, SZP, P],
+    'gnnb200_bn_finalize_f32': [P, P, I64, I64, c_float, c_float, P, P, P, P, P],
+    'gnnb200_bn_act_fwd_f32': [P, I64, P, P, P, P, c_int, c_float, c_uint64, I64, I64, P, I64, P],
+    'gnnb200_bn_act_bwd_f32': [P, I64, P, I64, P, P, P, P, c_int, c_float, c_uint64, c_int, I64, I64, P, I64, P, P, P, SZP, P],
     'gnnb200_lp_features_f32': [P, I64, P, I64, I64, P, I64, P],
     'gnnb200_lp_features_bwd_f32': [P, I64, P, I64, I64, P, I64, P, P, P, P, I64, P, I64, P],
     'gnnb200_ntxent_fwd_f32': [P, I64, I64, I64, c_float, P, P, P, P, P, SZP, P],

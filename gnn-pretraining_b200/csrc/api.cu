@@ -3,13 +3,14 @@
 
 namespace gnnb200 {
 int gemm_simt(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
-              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int epilogue, void* workspace,
-              size_t* workspace_bytes, cudaStream_t stream);
+              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
+              int epilogue, void* workspace, size_t* workspace_bytes, cudaStream_t stream);
 int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
-                        const float* C, int64_t ldc, int64_t M, int64_t N, int64_t K);
+                        const float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* residual,
+                        int64_t ldr);
 int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
-              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int epilogue, void* workspace,
-              size_t* workspace_bytes, cudaStream_t stream);
+              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
+              int epilogue, void* workspace, size_t* workspace_bytes, cudaStream_t stream);
 }  // namespace gnnb200
 
 extern "C" int gnnb200_version(void) { return 100; }
@@ -28,25 +29,25 @@ extern "C" const char* gnnb200_error_string(int code) {
 
 extern "C" int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
                                 float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
-                                int epilogue, int precision, void* workspace, size_t* workspace_bytes,
-                                gnnb200_stream_t stream_) {
+                                const float* residual, int64_t ldr, int epilogue, int precision, void* workspace,
+                                size_t* workspace_bytes, gnnb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (M < 0 || N < 0 || K < 0 || !workspace_bytes) return GNNB200_EINVAL;
   if (M >= (int64_t)INT32_MAX || N >= (int64_t)INT32_MAX) return GNNB200_ERANGE;
   if (workspace && M > 0 && N > 0 && (!C || (K > 0 && (!A || !B)))) return GNNB200_EINVAL;
   if (precision == GNNB200_GEMM_F32)
-    return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, epilogue, workspace,
-                              workspace_bytes, stream);
+    return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
+                              workspace, workspace_bytes, stream);
   if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_AUTO) {
     // the support predicate only reads sizes, leading dimensions and pointer alignment; during the
     // workspace query C may be NULL (NULL is 16-byte aligned), so both phases take the same branch
-    if (!gnnb200::gemm_tf32_supported(A, lda, transa, B, ldb, transb, C, ldc, M, N, K)) {
+    if (!gnnb200::gemm_tf32_supported(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, residual, ldr)) {
       if (precision == GNNB200_GEMM_TF32) return GNNB200_EUNSUPPORTED;
-      return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, epilogue, workspace,
-                                workspace_bytes, stream);
+      return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
+                                workspace, workspace_bytes, stream);
     }
-    return gnnb200::gemm_tf32(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, epilogue, workspace,
-                              workspace_bytes, stream);
+    return gnnb200::gemm_tf32(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
+                              workspace, workspace_bytes, stream);
   }
   return GNNB200_EINVAL;
 }

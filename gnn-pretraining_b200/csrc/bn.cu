@@ -1,0 +1,303 @@
+// Fused BatchNorm1d (+ReLU)(+dropout) over node rows (K4/K5 of SURVEY §2.4): the elementwise tail of
+// InputEncoder and GINLayer (reference src/models/gnn.py:19-22, :31-32, :41-43).  The reference runs
+// batch_norm, relu and dropout as separate passes that each read and write the [N, C] activation and
+// save their own copy for autograd; here one forward pass reads the pre-BN activation once and writes the
+// layer output once, and the backward recomputes x_hat / ReLU sign / dropout mask from the saved pre-BN
+// activation (nothing else is stored):
+//   finalize : (sum, m2, n) -> mean, invstd = rsqrt(m2/n + eps); running stats updated like torch
+//   fwd      : y = drop(relu((x - mean) * invstd * gamma + beta))
+//   bwd      : g1 = g * drop' * relu';  dbeta = sum g1;  dgamma = sum g1 * xhat          (two-stage, fixed order)
+//              dx = gamma * invstd * (g1 - dbeta/n - xhat * dgamma/n)
+// Dropout uses a counter-based Philox4x32-10 stream keyed by (seed, element index / 4): the same mask is
+// regenerated in the backward pass.  It is Bernoulli(1-p) with 1/(1-p) scaling like torch's, but not the
+// same bit stream as torch's CUDA generator (the reference's CPU and CUDA streams differ from each other too).
+#include "common.cuh"
+
+namespace gnnb200 {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// keep flags for the 4 consecutive elements starting at linear index 4*q
+__device__ __forceinline__ void keep4(uint64_t seed, uint64_t q, uint32_t thresh, bool (&k)[4]) {
+  const uint4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+  k[0] = r.x < thresh; k[1] = r.y < thresh; k[2] = r.z < thresh; k[3] = r.w < thresh;
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ m2, float n, float eps,
+                                   float momentum, int cols, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean,
+                                   float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const float mu = sum[c] / n;
+  const float var = m2[c] / n;
+  mean[c] = mu;
+  invstd[c] = rsqrtf(var + eps);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+  if (running_var) {
+    const float unbiased = n > 1.f ? m2[c] / (n - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+// One thread handles 4 consecutive columns of one row (cols % 4 == 0); grid-stride over rows*cols/4.
+template <bool DROP>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  int relu, uint64_t seed, uint32_t thresh, float scale, int64_t rows, int cols,
+                  float* __restrict__ y, int64_t ldy) {
+  const int c4 = cols >> 2;
+  const int64_t total = rows * c4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / c4;
+    const int c = (int)(q - r * c4) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float o[4] = {(v.x - mu.x) * is.x * ga.x + be.x, (v.y - mu.y) * is.y * ga.y + be.y,
+                  (v.z - mu.z) * is.z * ga.z + be.z, (v.w - mu.w) * is.w * ga.w + be.w};
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], 0.f);
+    }
+    if (DROP) {
+      bool k[4];
+      keep4(seed, (uint64_t)q, thresh, k);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = k[i] ? o[i] * scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+constexpr int kBnRows = 256;
+
+// g1 for element (r, c..c+3) recomputed from the saved pre-BN activation
+template <bool DROP>
+__device__ __forceinline__ void bn_g1(const float4 g, const float4 v, const float4 mu, const float4 is, const float4 ga,
+                                      const float4 be, int relu, uint64_t seed, uint64_t q, uint32_t thresh, float scale,
+                                      float (&g1)[4], float (&xh)[4]) {
+  const float gv[4] = {g.x, g.y, g.z, g.w};
+  xh[0] = (v.x - mu.x) * is.x; xh[1] = (v.y - mu.y) * is.y; xh[2] = (v.z - mu.z) * is.z; xh[3] = (v.w - mu.w) * is.w;
+  const float gav[4] = {ga.x, ga.y, ga.z, ga.w};
+  const float bev[4] = {be.x, be.y, be.z, be.w};
+  bool k[4] = {true, true, true, true};
+  if (DROP) keep4(seed, q, thresh, k);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t = gv[i];
+    if (DROP) t = k[i] ? t * scale : 0.f;
+    if (relu && !(xh[i] * gav[i] + bev[i] > 0.f)) t = 0.f;
+    g1[i] = t;
+  }
+}
+
+// Block = 32 column-quads (128 columns) x 8 row lanes over kBnRows rows; partial [chunks][2][cols].
+template <bool DROP>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, int relu, uint64_t seed,
+                         uint32_t thresh, float scale, int64_t rows, int cols, float* __restrict__ part) {
+  __shared__ float sm[2][8][128];
+  const int c4 = cols >> 2;
+  const int cq = blockIdx.x * 32 + threadIdx.x;     // column quad
+  const int c = cq << 2;
+  const int64_t r0 = (int64_t)blockIdx.y * kBnRows;
+  const int64_t r1 = min(rows, r0 + kBnRows);
+  float sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cq < c4) {
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + r * ldg + c);
+      const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      float g1[4], xh[4];
+      bn_g1<DROP>(gv, xv, mu, is, ga, be, relu, seed, (uint64_t)(r * c4 + cq), thresh, scale, g1, xh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { sb[i] += g1[i]; sg[i] = fmaf(g1[i], xh[i], sg[i]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sm[0][threadIdx.y][threadIdx.x * 4 + i] = sb[i];
+    sm[1][threadIdx.y][threadIdx.x * 4 + i] = sg[i];
+  }
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;       // 256 threads -> 2 x 128 outputs
+  const int which = t >> 7, col = t & 127;
+  if (blockIdx.x * 128 + col < cols) {
+    float acc = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc += sm[which][l][col];
+    part[((int64_t)blockIdx.y * 2 + which) * cols + blockIdx.x * 128 + col] = acc;
+  }
+}
+
+// Fold the chunk partials: 32 columns x 32 lanes per block, lanes stride the chunks in ascending order.
+__global__ void __launch_bounds__(1024)
+bn_act_bwd_finish_kernel(const float* __restrict__ part, int chunks, int cols, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta) {
+  __shared__ float sm[2][32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float b = 0.f, gsum = 0.f;
+  if (c < cols) {
+    for (int k = threadIdx.y; k < chunks; k += 32) {
+      b += part[((int64_t)k * 2 + 0) * cols + c];
+      gsum += part[((int64_t)k * 2 + 1) * cols + c];
+    }
+  }
+  sm[0][threadIdx.y][threadIdx.x] = b;
+  sm[1][threadIdx.y][threadIdx.x] = gsum;
+  __syncthreads();
+  if (threadIdx.y < 2 && c < cols) {
+    float acc = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) acc += sm[threadIdx.y][l][threadIdx.x];
+    (threadIdx.y == 0 ? dbeta : dgamma)[c] = acc;
+  }
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ dgamma, const float* __restrict__ dbeta, int relu, int training,
+                        uint64_t seed, uint32_t thresh, float scale, int64_t rows, int cols, float* __restrict__ dx,
+                        int64_t lddx) {
+  const int c4 = cols >> 2;
+  const int64_t total = rows * c4;
+  const float inv_n = 1.f / (float)rows;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / c4;
+    const int cq = (int)(q - r * c4);
+    const int c = cq << 2;
+    const float4 gv = *reinterpret_cast<const float4*>(g + r * ldg + c);
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float g1[4], xh[4];
+    bn_g1<DROP>(gv, xv, mu, is, ga, be, relu, seed, (uint64_t)q, thresh, scale, g1, xh);
+    const float isv[4] = {is.x, is.y, is.z, is.w};
+    const float gav[4] = {ga.x, ga.y, ga.z, ga.w};
+    float o[4];
+    if (training) {
+      const float4 dg = __ldg(reinterpret_cast<const float4*>(dgamma + c));
+      const float4 db = __ldg(reinterpret_cast<const float4*>(dbeta + c));
+      const float dgv[4] = {dg.x, dg.y, dg.z, dg.w};
+      const float dbv[4] = {db.x, db.y, db.z, db.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = gav[i] * isv[i] * (g1[i] - dbv[i] * inv_n - xh[i] * dgv[i] * inv_n);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = gav[i] * isv[i] * g1[i];     // eval mode: statistics are constants
+    }
+    *reinterpret_cast<float4*>(dx + r * lddx + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static inline int ew_grid(int64_t work) {
+  int64_t g = (work + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+static inline bool bn_layout_ok(int64_t cols, int64_t lda, int64_t ldb, const void* a, const void* b) {
+  return cols % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
+}
+
+}  // namespace gnnb200
+
+using namespace gnnb200;
+
+extern "C" int gnnb200_bn_finalize_f32(const float* sum, const float* m2, int64_t rows, int64_t cols, float eps,
+                                       float momentum, float* running_mean, float* running_var, float* mean,
+                                       float* invstd, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows <= 0 || cols < 0) return GNNB200_EINVAL;
+  if (cols == 0) return GNNB200_OK;
+  if (!sum || !m2 || !mean || !invstd) return GNNB200_EINVAL;
+  bn_finalize_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(sum, m2, (float)rows, eps, momentum, (int)cols,
+                                                                        running_mean, running_var, mean, invstd);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+extern "C" int gnnb200_bn_act_fwd_f32(const float* x, int64_t ldx, const float* mean, const float* invstd,
+                                      const float* gamma, const float* beta, int relu, float drop_p, uint64_t seed,
+                                      int64_t rows, int64_t cols, float* y, int64_t ldy, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows < 0 || cols < 0 || !(drop_p >= 0.f && drop_p < 1.f)) return GNNB200_EINVAL;
+  if (rows == 0 || cols == 0) return GNNB200_OK;
+  if (!x || !mean || !invstd || !gamma || !beta || !y) return GNNB200_EINVAL;
+  if (!bn_layout_ok(cols, ldx, ldy, x, y)) return GNNB200_EUNSUPPORTED;
+  const uint32_t thresh = (uint32_t)((double)(1.f - drop_p) * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)(1.f - drop_p) * 4294967296.0);
+  const float scale = 1.f / (1.f - drop_p);
+  const int grid = ew_grid(rows * (cols / 4));
+  if (drop_p > 0.f)
+    bn_act_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, mean, invstd, gamma, beta, relu, seed, thresh, scale, rows, (int)cols, y, ldy);
+  else
+    bn_act_fwd_kernel<false><<<grid, 256, 0, stream>>>(x, ldx, mean, invstd, gamma, beta, relu, seed, thresh, scale, rows, (int)cols, y, ldy);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+extern "C" int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const float* x, int64_t ldx, const float* mean,
+                                      const float* invstd, const float* gamma, const float* beta, int relu,
+                                      float drop_p, uint64_t seed, int training, int64_t rows, int64_t cols,
+                                      float* grad_x, int64_t ldgx, float* dgamma, float* dbeta, void* workspace,
+                                      size_t* workspace_bytes, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows < 0 || cols < 0 || !workspace_bytes || !(drop_p >= 0.f && drop_p < 1.f)) return GNNB200_EINVAL;
+  const int64_t chunks = rows > 0 ? (rows + kBnRows - 1) / kBnRows : 1;
+  if (chunks > 65535) return GNNB200_ERANGE;
+  Workspace ws(workspace);
+  float* part = ws.take<float>((size_t)chunks * 2 * cols);
+  if (!workspace) {
+    *workspace_bytes = ws.bytes();
+    return GNNB200_OK;
+  }
+  if (*workspace_bytes < ws.bytes()) return GNNB200_EWORKSPACE;
+  if (rows == 0 || cols == 0) return GNNB200_OK;
+  if (!grad_y || !x || !mean || !invstd || !gamma || !beta || !grad_x || !dgamma || !dbeta) return GNNB200_EINVAL;
+  if (!bn_layout_ok(cols, ldg, ldx, grad_y, x) || ldgx % 4 != 0 || ((uintptr_t)grad_x % 16) != 0) return GNNB200_EUNSUPPORTED;
+  const uint32_t thresh = (uint32_t)((double)(1.f - drop_p) * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)(1.f - drop_p) * 4294967296.0);
+  const float scale = 1.f / (1.f - drop_p);
+  const bool drop = drop_p > 0.f;
+  dim3 rgrid((unsigned)((cols + 127) / 128), (unsigned)chunks);
+  dim3 rblock(32, 8);
+  if (drop)
+    bn_act_bwd_reduce_kernel<true><<<rgrid, rblock, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, relu, seed, thresh, scale, rows, (int)cols, part);
+  else
+    bn_act_bwd_reduce_kernel<false><<<rgrid, rblock, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, relu, seed, thresh, scale, rows, (int)cols, part);
+  GNNB200_LAUNCH_CHECK();
+  bn_act_bwd_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)chunks, (int)cols, dgamma, dbeta);
+  GNNB200_LAUNCH_CHECK();
+  const int grid = ew_grid(rows * (cols / 4));
+  if (drop)
+    bn_act_bwd_apply_kernel<true><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, (int)cols, grad_x, ldgx);
+  else
+    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, (int)cols, grad_x, ldgx);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}

@@ -14,7 +14,8 @@ template <bool A_KCONTIG, bool B_NCONTIG>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbk,
                  int64_t sbn, float* __restrict__ C, int64_t ldc, int M, int N, int64_t K, int64_t k_per_split,
-                 const float* __restrict__ bias, int relu, float* __restrict__ partial) {
+                 const float* __restrict__ bias, const float* __restrict__ residual, int64_t ldr, int relu,
+                 float* __restrict__ partial) {
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
@@ -97,6 +98,7 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
       } else {
         float v = acc[i][j];
         if (bias) v += bias[gn];
+        if (residual) v += residual[(int64_t)gm * ldr + gn];
         if (relu) v = fmaxf(v, 0.f);
         C[(int64_t)gm * ldc + gn] = v;
       }
@@ -106,13 +108,14 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
 
 __global__ void __launch_bounds__(256)
 gemm_splitk_finish_kernel(const float* __restrict__ partial, int splits, int M, int N, const float* __restrict__ bias,
-                          int relu, float* __restrict__ C, int64_t ldc) {
+                          const float* __restrict__ residual, int64_t ldr, int relu, float* __restrict__ C, int64_t ldc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
   const int m = (int)(i / N), n = (int)(i % N);
   float v = 0.f;
   for (int s = 0; s < splits; ++s) v += partial[(int64_t)s * M * N + i];
   if (bias) v += bias[n];
+  if (residual) v += residual[(int64_t)m * ldr + n];
   if (relu) v = fmaxf(v, 0.f);
   C[(int64_t)m * ldc + n] = v;
 }
@@ -128,8 +131,8 @@ int gemm_simt_splits(int64_t M, int64_t N, int64_t K) {
 }
 
 int gemm_simt(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
-              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int epilogue, void* workspace,
-              size_t* workspace_bytes, cudaStream_t stream) {
+              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
+              int epilogue, void* workspace, size_t* workspace_bytes, cudaStream_t stream) {
   const int splits = gemm_simt_splits(M, N, K);
   Workspace ws(workspace);
   float* partial = splits > 1 ? ws.take<float>((size_t)splits * M * N) : nullptr;
@@ -151,7 +154,7 @@ int gemm_simt(const float* A, int64_t lda, int transa, const float* B, int64_t l
   const bool ak = !transa, bn = !transb;
 #define GNNB200_SIMT_LAUNCH(AK, BNC)                                                                             \
   gemm_simt_kernel<AK, BNC><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, K, kps, \
-                                                      bias, relu, partial)
+                                                      bias, residual, ldr, relu, partial)
   if (ak && bn) GNNB200_SIMT_LAUNCH(true, true);
   else if (ak && !bn) GNNB200_SIMT_LAUNCH(true, false);
   else if (!ak && bn) GNNB200_SIMT_LAUNCH(false, true);
@@ -161,7 +164,7 @@ int gemm_simt(const float* A, int64_t lda, int transa, const float* B, int64_t l
   if (splits > 1) {
     const int64_t total = M * N;
     gemm_splitk_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splits, (int)M, (int)N,
-                                                                                  bias, relu, C, ldc);
+                                                                                  bias, residual, ldr, relu, C, ldc);
     GNNB200_LAUNCH_CHECK();
   }
   return GNNB200_OK;

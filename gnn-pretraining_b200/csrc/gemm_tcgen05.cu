@@ -128,6 +128,8 @@ struct Params {
   float* C;          // output, or the split-K partial buffer [splits][M][N]
   long long ldc;
   const float* bias;  // applied only when splits == 1
+  const float* residual;  // [M,N] added in the epilogue (GINLayer's `+ h`), only when splits == 1
+  long long ldr;
   int relu;
 };
 
@@ -287,6 +289,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                   o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
+                if (p.residual) {
+                  const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col));
+                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
                 if (p.relu) {
                   o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
@@ -313,7 +319,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long mn, int N, const float* __restrict__ bias,
-                     int relu, float* __restrict__ C, long long ldc) {
+                     const float* __restrict__ residual, long long ldr, int relu, float* __restrict__ C, long long ldc) {
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= mn) return;
   float4 acc = *reinterpret_cast<const float4*>(partial + i4);
@@ -326,6 +332,10 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long mn
   if (bias) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
     acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+  }
+  if (residual) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(residual + m * ldr + n));
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
   }
   if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
   *reinterpret_cast<float4*>(C + m * ldc + n) = acc;
@@ -414,7 +424,9 @@ static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensor
 }  // namespace tc
 
 int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
-                        const float* C, int64_t ldc, int64_t M, int64_t N, int64_t K) {
+                        const float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* residual,
+                        int64_t ldr) {
+  if (residual && (ldr % 4 != 0 || ((uintptr_t)residual & 15))) return 0;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (N % 4 != 0 || N < 8) return 0;
   if (lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0) return 0;
@@ -425,8 +437,8 @@ int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B,
 }
 
 int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
-              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int epilogue, void* workspace,
-              size_t* workspace_bytes, cudaStream_t stream) {
+              int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
+              int epilogue, void* workspace, size_t* workspace_bytes, cudaStream_t stream) {
   using namespace tc;
   const int bn = pick_bn(N);
   const int m_tiles = (int)((M + BM - 1) / BM);
@@ -468,6 +480,8 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   p.C = splits > 1 ? partial : C;
   p.ldc = splits > 1 ? N : ldc;
   p.bias = splits > 1 ? nullptr : bias;
+  p.residual = splits > 1 ? nullptr : residual;
+  p.ldr = ldr;
   p.relu = (splits == 1 && (epilogue & GNNB200_EPI_RELU)) ? 1 : 0;
   const long long total = tiles * splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
@@ -477,7 +491,7 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   if (rc) return rc;
   if (splits > 1) {
     const long long mn = (long long)M * N;
-    splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, stream>>>(partial, splits, mn, (int)N, bias,
+    splitk_reduce_kernel<<<(unsigned)((mn / 4 + 255) / 256), 256, 0, stream>>>(partial, splits, mn, (int)N, bias, residual, ldr,
                                                                                (epilogue & GNNB200_EPI_RELU) ? 1 : 0, C, ldc);
     GNNB200_LAUNCH_CHECK();
   }

@@ -116,19 +116,30 @@ colstats_partial_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, 
   }
 }
 
-__global__ void __launch_bounds__(128)
+// Merge the per-chunk partials of 32 columns per block: 32 row lanes each fold a strided subset of the
+// chunks in ascending order, then the 32 lane results are folded in lane order (fixed order -> same bits).
+__global__ void __launch_bounds__(1024)
 colstats_finish_kernel(const float* __restrict__ part, int chunks, int cols, float* __restrict__ sum,
                        float* __restrict__ m2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ Moments sm[32][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   Moments t = {0.f, 0.f, 0.f};
-  for (int k = 0; k < chunks; ++k) {
-    const float* p = part + (int64_t)k * 3 * cols;
-    Moments b = {p[c], p[cols + c], p[2 * cols + c]};
-    t = merge(t, b);
+  if (c < cols) {
+    for (int k = threadIdx.y; k < chunks; k += 32) {
+      const float* p = part + (int64_t)k * 3 * cols;
+      Moments b = {p[c], p[cols + c], p[2 * cols + c]};
+      t = merge(t, b);
+    }
   }
-  if (sum) sum[c] = t.sum;
-  if (m2) m2[c] = t.m2;
+  sm[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    Moments r = sm[0][threadIdx.x];
+#pragma unroll
+    for (int l = 1; l < 32; ++l) r = merge(r, sm[l][threadIdx.x]);
+    if (sum) sum[c] = r.sum;
+    if (m2) m2[c] = r.m2;
+  }
 }
 
 }  // namespace gnnb200
@@ -177,7 +188,7 @@ extern "C" int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, i
   dim3 block(128, 4);
   colstats_partial_kernel<<<grid, block, 0, stream>>>(x, ldx, rows, (int)cols, part);
   GNNB200_LAUNCH_CHECK();
-  colstats_finish_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(part, (int)chunks, (int)cols, sum, m2);
+  colstats_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)chunks, (int)cols, sum, m2);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }

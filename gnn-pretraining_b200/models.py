@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import ops
-from .nn import GINConv, Linear, global_mean_pool
+from .nn import BatchNormAct, FusedAwayReLU, GINConv, Linear, global_mean_pool
 
 # constants of the reference (src/models/gnn.py:6-8, heads.py:10-13, pretrain_model.py:18-20,
 # finetune_model.py:14-17, src/data/data_setup.py:24-59, src/data/graph_properties.py:13)
@@ -47,11 +47,12 @@ class InputEncoder(nn.Module):
     def __init__(self, dim_in: int, hidden_dim: int = GNN_HIDDEN_DIM) -> None:
         super().__init__()
         self.linear = Linear(dim_in, hidden_dim)
-        self.batch_norm = nn.BatchNorm1d(hidden_dim)
+        self.batch_norm = BatchNormAct(hidden_dim, relu=True)
         self.dropout = nn.Dropout(DROPOUT_RATE)
 
     def forward(self, x: Tensor) -> Tensor:
-        return self.dropout(F.relu(self.batch_norm(self.linear(x))))
+        # Linear -> [BatchNorm + ReLU + Dropout in one pass]; p follows self.dropout.p like the reference
+        return self.batch_norm(self.linear(x), drop_p=self.dropout.p)
 
 
 class GINLayer(nn.Module):
@@ -60,15 +61,18 @@ class GINLayer(nn.Module):
     def __init__(self, hidden_dim: int = GNN_HIDDEN_DIM) -> None:
         super().__init__()
         self.gin_conv = GINConv(
-            nn.Sequential(Linear(hidden_dim, 2 * hidden_dim), nn.BatchNorm1d(2 * hidden_dim), nn.ReLU(),
+            nn.Sequential(Linear(hidden_dim, 2 * hidden_dim), BatchNormAct(2 * hidden_dim, relu=True), FusedAwayReLU(),
                           Linear(2 * hidden_dim, hidden_dim)),
             train_eps=True)
-        self.batch_norm = nn.BatchNorm1d(hidden_dim)
+        self.batch_norm = BatchNormAct(hidden_dim, relu=True)
 
     def forward(self, h: Tensor, edge_index: Tensor) -> Tensor:
-        z = self.gin_conv(h, edge_index) + h
-        z = F.relu(self.batch_norm(z))
-        return F.dropout(z, p=DROPOUT_RATE, training=self.training)
+        # 5 kernels per layer forward: gather(+self term) -> GEMM -> BN+ReLU -> GEMM(+residual h) -> BN+ReLU+dropout
+        mlp = self.gin_conv.nn
+        z = self.gin_conv.aggregate(h, edge_index)
+        z = mlp[2](mlp[1](mlp[0](z)))
+        z = mlp[3](z, residual=h)
+        return self.batch_norm(z, drop_p=DROPOUT_RATE)
 
 
 class GINBackbone(nn.Module):

@@ -62,6 +62,7 @@ KERNELS_PER_CALL = {
     'gnnb200_aggregate_f32': 1, 'gnnb200_dot_f32': 2, 'gnnb200_segment_pool_fwd_f32': 1,
     'gnnb200_segment_pool_bwd_f32': 1, 'gnnb200_rows_gather_f32': 1, 'gnnb200_rows_scatter_f32': 1,
     'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_colstats_f32': 2,
+    'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1,
 }
@@ -395,8 +396,8 @@ PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_AUTO, 'tf32_strict': L.GEMM_TF32
 
 
 def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor], relu: bool,
-              precision: int) -> Tensor:
-    _need_cuda(a, b, bias)
+              precision: int, residual: Optional[Tensor] = None) -> Tensor:
+    _need_cuda(a, b, bias, residual)
     a, b = _rowmajor(a), _rowmajor(b)
     M, K = (a.size(1), a.size(0)) if transa else (a.size(0), a.size(1))
     Kb, N = (b.size(1), b.size(0)) if transb else (b.size(0), b.size(1))
@@ -405,9 +406,13 @@ def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[T
     c = torch.empty(M, N, dtype=torch.float32, device=a.device)
     if bias is not None:
         bias = bias.contiguous()
+    if residual is not None:
+        residual = _rowmajor(residual)
+        if residual.shape != c.shape:
+            raise L.Gnnb200Error(f'residual shape {tuple(residual.shape)} != output shape {tuple(c.shape)}')
     _call_ws('gnnb200_gemm_f32', 'gemm', a.device, _ptr(a), _ld(a), int(transa), _ptr(b), _ld(b), int(transb),
-             _ptr(c), _ld(c), M, N, K, _ptr(bias), L.EPI_RELU if relu else L.EPI_NONE, precision,
-             stream=_stream(a))
+             _ptr(c), _ld(c), M, N, K, _ptr(bias), _ptr(residual), _ld(residual) if residual is not None else 0,
+             L.EPI_RELU if relu else L.EPI_NONE, precision, stream=_stream(a))
     return c
 
 
@@ -459,20 +464,23 @@ def _(x):
 
 
 @torch.library.custom_op('gnnb200::linear', mutates_args=())
-def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int) -> Tensor:
-    """y = x W^T + b with W [out, in] (nn.Linear layout)."""
-    return _gemm_raw(x, False, weight, True, bias, False, precision)
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int,
+           residual: Optional[Tensor] = None) -> Tensor:
+    """y = x W^T + b (+ residual) with W [out, in] (nn.Linear layout); the residual add (GINLayer's
+    `gin_conv(h) + h`) happens in the GEMM epilogue."""
+    return _gemm_raw(x, False, weight, True, bias, False, precision, residual)
 
 
 @linear.register_fake
-def _(x, weight, bias, precision):
+def _(x, weight, bias, precision, residual=None):
     return x.new_empty(x.size(0), weight.size(0))
 
 
 def _lin_setup(ctx, inputs, output):
-    x, weight, bias, precision = inputs
+    x, weight, bias, precision, residual = inputs
     ctx.precision = precision
     ctx.has_bias = bias is not None
+    ctx.has_residual = residual is not None
     ctx.save_for_backward(x, weight)
 
 
@@ -486,10 +494,96 @@ def _lin_backward(ctx, g):
         gw = gemm(g, True, x, False, None, False, ctx.precision)            # [out,M] x [M,in]
     if ctx.has_bias and ctx.needs_input_grad[2]:
         gb = colsum(g)
-    return gx, gw, gb, None
+    gres = g if (ctx.has_residual and ctx.needs_input_grad[4]) else None
+    return gx, gw, gb, None, gres
 
 
 linear.register_autograd(_lin_backward, setup_context=_lin_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused BatchNorm1d (+ReLU)(+dropout)
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op('gnnb200::bn_batch_stats', mutates_args=('running_mean', 'running_var'))
+def bn_batch_stats(x: Tensor, running_mean: Optional[Tensor], running_var: Optional[Tensor], momentum: float,
+                   eps: float) -> Tuple[Tensor, Tensor]:
+    """(mean, invstd) over the rows of x; the running buffers are updated in place with torch's rule
+    (momentum, unbiased variance).  Not differentiable by itself: bn_act's backward carries the full
+    batch-statistics Jacobian."""
+    _need_cuda(x, running_mean, running_var)
+    x = _rowmajor(x)
+    rows, cols = x.shape
+    dev = x.device
+    st = _stream(x)
+    s = torch.empty(cols, dtype=torch.float32, device=dev)
+    m2 = torch.empty(cols, dtype=torch.float32, device=dev)
+    _call_ws('gnnb200_colstats_f32', 'bn colstats', dev, _ptr(x), _ld(x), rows, cols, _ptr(s), _ptr(m2), stream=st)
+    mean = torch.empty(cols, dtype=torch.float32, device=dev)
+    invstd = torch.empty(cols, dtype=torch.float32, device=dev)
+    L.check(_invoke('gnnb200_bn_finalize_f32', _ptr(s), _ptr(m2), rows, cols, eps, momentum, _ptr(running_mean),
+                    _ptr(running_var), _ptr(mean), _ptr(invstd), st), 'bn_finalize')
+    return mean, invstd
+
+
+@bn_batch_stats.register_fake
+def _(x, running_mean, running_var, momentum, eps):
+    return x.new_empty(x.size(1)), x.new_empty(x.size(1))
+
+
+@torch.library.custom_op('gnnb200::bn_act', mutates_args=())
+def bn_act(x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, relu: bool, drop_p: float,
+           seed: int, training: bool) -> Tensor:
+    """y = drop(relu((x - mean) * invstd * gamma + beta)).  training=True means mean/invstd are the batch
+    statistics of x (the backward then includes their Jacobian); False = constants (eval mode)."""
+    _need_cuda(x, mean, invstd, gamma, beta)
+    x = _rowmajor(x)
+    rows, cols = x.shape
+    y = torch.empty(rows, cols, dtype=torch.float32, device=x.device)
+    L.check(_invoke('gnnb200_bn_act_fwd_f32', _ptr(x), _ld(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta),
+                    int(relu), drop_p, seed, rows, cols, _ptr(y), _ld(y), _stream(x)), 'bn_act_fwd')
+    return y
+
+
+@bn_act.register_fake
+def _(x, mean, invstd, gamma, beta, relu, drop_p, seed, training):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op('gnnb200::bn_act_bwd', mutates_args=())
+def bn_act_bwd(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, relu: bool,
+               drop_p: float, seed: int, training: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(grad_y, x, mean, invstd, gamma, beta)
+    g, x = _rowmajor(grad_y), _rowmajor(x)
+    rows, cols = x.shape
+    dev = x.device
+    gx = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+    dgamma = torch.empty(cols, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(cols, dtype=torch.float32, device=dev)
+    _call_ws('gnnb200_bn_act_bwd_f32', 'bn_act_bwd', dev, _ptr(g), _ld(g), _ptr(x), _ld(x), _ptr(mean), _ptr(invstd),
+             _ptr(gamma), _ptr(beta), int(relu), drop_p, seed, int(training), rows, cols, _ptr(gx), _ld(gx),
+             _ptr(dgamma), _ptr(dbeta), stream=_stream(x))
+    return gx, dgamma, dbeta
+
+
+@bn_act_bwd.register_fake
+def _(grad_y, x, mean, invstd, gamma, beta, relu, drop_p, seed, training):
+    return torch.empty_like(x), x.new_empty(x.size(1)), x.new_empty(x.size(1))
+
+
+def _bn_setup(ctx, inputs, output):
+    x, mean, invstd, gamma, beta, relu, drop_p, seed, training = inputs
+    ctx.cfg = (relu, drop_p, seed, training)
+    ctx.save_for_backward(x, mean, invstd, gamma, beta)
+
+
+def _bn_backward(ctx, gy):
+    x, mean, invstd, gamma, beta = ctx.saved_tensors
+    relu, drop_p, seed, training = ctx.cfg
+    gx, dgamma, dbeta = bn_act_bwd(gy.contiguous(), x, mean, invstd, gamma, beta, relu, drop_p, seed, training)
+    return gx, None, None, dgamma, dbeta, None, None, None, None
+
+
+bn_act.register_autograd(_bn_backward, setup_context=_bn_setup)
 
 
 # ---------------------------------------------------------------------------------------------

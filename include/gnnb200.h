@@ -123,7 +123,8 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
 
 /* ------------------------------------------------------------------------------------------
  * Dense transforms (K3: nn.Linear of src/models/gnn.py:13,31,34 and src/models/heads.py:41).
- *   C[M,N] = op(A) * op(B) (+ bias[N]) (ReLU)        op = identity or transpose
+ *   C[M,N] = op(A) * op(B) (+ bias[N]) (+ residual[M,N]) (ReLU)        op = identity or transpose
+ *   (residual fuses GINLayer's `gin_conv(h) + h`, src/models/gnn.py:41; may be NULL)
  *   A is [M,K] (transa=0) or [K,M] (transa=1); B is [K,N] (transb=0) or [N,K] (transb=1).
  * precision: F32 = fp32 FFMA (1e-5 class); TF32 = tcgen05.mma kind::tf32 with TMA-fed
  * shared-memory tiles and TMEM fp32 accumulators (2e-2 class).  TF32 needs a TMA-legal
@@ -136,14 +137,37 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
 #define GNNB200_EPI_RELU 1
 int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
                      float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
-                     int epilogue, int precision, void* workspace, size_t* workspace_bytes,
-                     gnnb200_stream_t stream);
+                     const float* residual, int64_t ldr, int epilogue, int precision, void* workspace,
+                     size_t* workspace_bytes, gnnb200_stream_t stream);
 
 /* Column statistics over rows (K4 BatchNorm1d batch stats of src/models/gnn.py:15,32,38 and bias
  * gradients): sum[c] = sum_r x[r,c]; when sumsq != NULL also the centred second moment
  * m2[c] = sum_r (x[r,c]-mean_c)^2 (Chan merge of per-block Welford partials). */
 int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* sum,
                          float* m2, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused BatchNorm1d (+ReLU)(+dropout) over node rows (K4/K5: src/models/gnn.py:19-22,31-32,41-43).
+ *   finalize: mean = sum/rows, invstd = rsqrt(m2/rows + eps); running stats (may be NULL) updated
+ *             like torch (momentum, unbiased variance).  sum/m2 come from gnnb200_colstats_f32.
+ *   fwd     : y = drop(relu((x - mean) * invstd * gamma + beta)); dropout is Bernoulli(1-p) with
+ *             1/(1-p) scaling from a Philox4x32-10 stream keyed by (seed, element index).
+ *   bwd     : recomputes x_hat / ReLU sign / dropout mask from x (the saved pre-BN activation);
+ *             writes grad_x, dgamma, dbeta (two-stage fixed-order column reductions).
+ *             training = 0 treats mean/invstd as constants (eval mode).
+ * cols % 4 == 0 and 16-byte aligned rows are required (GNNB200_EUNSUPPORTED otherwise).
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_bn_finalize_f32(const float* sum, const float* m2, int64_t rows, int64_t cols, float eps,
+                            float momentum, float* running_mean, float* running_var, float* mean,
+                            float* invstd, gnnb200_stream_t stream);
+int gnnb200_bn_act_fwd_f32(const float* x, int64_t ldx, const float* mean, const float* invstd,
+                           const float* gamma, const float* beta, int relu, float drop_p, uint64_t seed,
+                           int64_t rows, int64_t cols, float* y, int64_t ldy, gnnb200_stream_t stream);
+int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const float* x, int64_t ldx, const float* mean,
+                           const float* invstd, const float* gamma, const float* beta, int relu, float drop_p,
+                           uint64_t seed, int training, int64_t rows, int64_t cols, float* grad_x, int64_t ldgx,
+                           float* dgamma, float* dbeta, void* workspace, size_t* workspace_bytes,
+                           gnnb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Link-prediction decoder input (K8, src/models/heads.py:59-65): for each edge (u,v)

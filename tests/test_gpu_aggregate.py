@@ -18,6 +18,16 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
+@pytest.fixture(autouse=True)
+def _f32_default():
+    """These tests check the 1e-5 class: module-level Linear layers use the fp32 FFMA GEMM here."""
+    from gnnb200 import nn as gnn
+    old = gnn.default_precision()
+    gnn.set_default_precision('f32')
+    yield
+    gnn.set_default_precision(old)
+
+
 def _graph(n, e, seed):
     g = torch.Generator().manual_seed(seed)
     return torch.randint(0, n, (2, e), generator=g)

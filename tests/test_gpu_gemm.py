@@ -9,6 +9,16 @@ from gnnb200.nn import Linear
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
+
+
+@pytest.fixture(autouse=True)
+def _f32_default():
+    """These tests check the 1e-5 class: module-level Linear layers use the fp32 FFMA GEMM here."""
+    from gnnb200 import nn as gnn
+    old = gnn.default_precision()
+    gnn.set_default_precision('f32')
+    yield
+    gnn.set_default_precision(old)
 TOL_F32 = 1e-5      # north_star: 1e-5 relative for fp32 paths
 TOL_TF32 = 2e-2     # north_star: 2e-2 for reduced-precision GEMM paths
 
@@ -140,3 +150,26 @@ def test_tf32_falls_back_to_ffma_only_for_illegal_layouts():
         ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32_strict'])
     got = ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32'])
     assert _rel(got, a.double().cpu() @ w.double().cpu().t()) < TOL_F32
+
+
+@pytest.mark.parametrize('prec', ['f32', 'tf32'])
+def test_linear_residual_epilogue(prec):
+    """GINLayer's `gin_conv(h) + h` is folded into the GEMM epilogue; the residual gets the identity gradient."""
+    g = torch.Generator().manual_seed(6)
+    ref = torch.nn.Linear(512, 256)
+    lin = Linear(512, 256)
+    lin.precision = prec
+    lin.load_state_dict(ref.state_dict())
+    lin = lin.to(DEV)
+    x = torch.randn(3000, 512, generator=g)
+    h = torch.randn(3000, 256, generator=g)
+    go = torch.randn(3000, 256, generator=g)
+    xr, hr = x.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    (ref(xr) + hr).backward(go)
+    xg, hg = x.to(DEV).requires_grad_(True), h.to(DEV).requires_grad_(True)
+    y = lin(xg, residual=hg)
+    y.backward(go.to(DEV))
+    tol = TOL_F32 if prec == 'f32' else 5e-3
+    assert _rel(y, (ref(x) + h).detach()) < tol
+    assert _rel(xg.grad, xr.grad) < tol
+    assert torch.equal(hg.grad.cpu(), go)
