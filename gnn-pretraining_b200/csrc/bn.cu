@@ -180,11 +180,11 @@ bn_act_bwd_apply_kernel(const float* __restrict__ g, int64_t ldg, const float* _
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         const float* __restrict__ dgamma, const float* __restrict__ dbeta, int relu, int training,
-                        uint64_t seed, uint32_t thresh, float scale, int64_t rows, int cols, float* __restrict__ dx,
-                        int64_t lddx) {
+                        uint64_t seed, uint32_t thresh, float scale, int64_t rows, int64_t rows_total, int cols,
+                        float* __restrict__ dx, int64_t lddx) {
   const int c4 = cols >> 2;
   const int64_t total = rows * c4;
-  const float inv_n = 1.f / (float)rows;
+  const float inv_n = 1.f / (float)rows_total;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = q / c4;
     const int cq = (int)(q - r * c4);
@@ -264,11 +264,14 @@ extern "C" int gnnb200_bn_act_fwd_f32(const float* x, int64_t ldx, const float* 
 
 extern "C" int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const float* x, int64_t ldx, const float* mean,
                                       const float* invstd, const float* gamma, const float* beta, int relu,
-                                      float drop_p, uint64_t seed, int training, int64_t rows, int64_t cols,
-                                      float* grad_x, int64_t ldgx, float* dgamma, float* dbeta, void* workspace,
-                                      size_t* workspace_bytes, gnnb200_stream_t stream_) {
+                                      float drop_p, uint64_t seed, int training, int phase, int64_t rows,
+                                      int64_t rows_total, int64_t cols, float* grad_x, int64_t ldgx, float* dgamma,
+                                      float* dbeta, void* workspace, size_t* workspace_bytes,
+                                      gnnb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (rows < 0 || cols < 0 || !workspace_bytes || !(drop_p >= 0.f && drop_p < 1.f)) return GNNB200_EINVAL;
+  if (rows < 0 || cols < 0 || !workspace_bytes || !(drop_p >= 0.f && drop_p < 1.f) || phase < 0 || phase > 2 ||
+      rows_total < rows)
+    return GNNB200_EINVAL;
   const int64_t chunks = rows > 0 ? (rows + kBnRows - 1) / kBnRows : 1;
   if (chunks > 65535) return GNNB200_ERANGE;
   Workspace ws(workspace);
@@ -279,13 +282,14 @@ extern "C" int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const fl
   }
   if (*workspace_bytes < ws.bytes()) return GNNB200_EWORKSPACE;
   if (rows == 0 || cols == 0) return GNNB200_OK;
-  if (!grad_y || !x || !mean || !invstd || !gamma || !beta || !grad_x || !dgamma || !dbeta) return GNNB200_EINVAL;
-  if (!bn_layout_ok(cols, ldg, ldx, grad_y, x) || ldgx % 4 != 0 || ((uintptr_t)grad_x % 16) != 0) return GNNB200_EUNSUPPORTED;
+  if (!grad_y || !x || !mean || !invstd || !gamma || !beta || !dgamma || !dbeta || (phase != 1 && !grad_x)) return GNNB200_EINVAL;
+  if (!bn_layout_ok(cols, ldg, ldx, grad_y, x) || (phase != 1 && (ldgx % 4 != 0 || ((uintptr_t)grad_x % 16) != 0))) return GNNB200_EUNSUPPORTED;
   const uint32_t thresh = (uint32_t)((double)(1.f - drop_p) * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)(1.f - drop_p) * 4294967296.0);
   const float scale = 1.f / (1.f - drop_p);
   const bool drop = drop_p > 0.f;
   dim3 rgrid((unsigned)((cols + 127) / 128), (unsigned)chunks);
   dim3 rblock(32, 8);
+  if (phase == 2) goto apply;
   if (drop)
     bn_act_bwd_reduce_kernel<true><<<rgrid, rblock, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, relu, seed, thresh, scale, rows, (int)cols, part);
   else
@@ -293,11 +297,14 @@ extern "C" int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const fl
   GNNB200_LAUNCH_CHECK();
   bn_act_bwd_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)chunks, (int)cols, dgamma, dbeta);
   GNNB200_LAUNCH_CHECK();
+  if (phase == 1) return GNNB200_OK;
+apply : {
   const int grid = ew_grid(rows * (cols / 4));
   if (drop)
-    bn_act_bwd_apply_kernel<true><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, (int)cols, grad_x, ldgx);
+    bn_act_bwd_apply_kernel<true><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, rows_total, (int)cols, grad_x, ldgx);
   else
-    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, (int)cols, grad_x, ldgx);
+    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, rows_total, (int)cols, grad_x, ldgx);
   GNNB200_LAUNCH_CHECK();
+}
   return GNNB200_OK;
 }

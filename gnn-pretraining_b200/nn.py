@@ -15,6 +15,8 @@ from .graph import graph_of, segment_ptr_of
 # the north star's 2e-2 tolerance class) wherever TMA's layout rules hold, FFMA elsewhere;
 # 'f32' = FFMA everywhere (1e-5 class).
 _default_precision = 'tf32'
+# node-partitioned execution (gnnb200.partition.partition_scope sets this to the rank's PartitionedGraph)
+_partition = None
 
 
 def set_default_precision(name: str) -> None:
@@ -70,6 +72,15 @@ class BatchNormAct(torch.nn.BatchNorm1d):
         if use_batch_stats and self.training and self.num_batches_tracked is not None:
             self.num_batches_tracked.add_(1)
         seed = _dropout_seed() if p > 0.0 else 0
+        if use_batch_stats and _partition is not None:
+            from . import partition as part        # x is this rank's row shard: reduce the statistics over ranks
+            upd = self.training and self.track_running_stats
+            seed ^= (_partition.rank * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)      # independent masks per shard
+            mean, invstd = part.synced_batch_stats(x, _partition.num_nodes, ops.SYNC_GROUP,
+                                                   self.running_mean if upd else None, self.running_var if upd else None,
+                                                   float(self.momentum if self.momentum is not None else 0.0), float(self.eps))
+            return ops.bn_act(x, mean, invstd, self.weight, self.bias, self.fused_relu, p, seed, True,
+                              _partition.num_nodes)
         if use_batch_stats:
             upd = self.training and self.track_running_stats
             mean, invstd = ops.bn_batch_stats(x.detach(), self.running_mean if upd else None,
@@ -124,7 +135,10 @@ class GINConv(torch.nn.Module):
         _reset(self.nn)
         self.eps.data.fill_(self.initial_eps)
 
-    def aggregate(self, x: Tensor, edge_index: Tensor) -> Tensor:
+    def aggregate(self, x: Tensor, edge_index) -> Tensor:
+        if not isinstance(edge_index, Tensor):     # a gnnb200.partition.PartitionedGraph
+            from .partition import partitioned_gin_aggregate
+            return partitioned_gin_aggregate(x, self.eps, edge_index)
         g = graph_of(edge_index, x.size(0))
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or self.eps.requires_grad)
         if needs_grad:

@@ -532,9 +532,11 @@ def _(x, running_mean, running_var, momentum, eps):
 
 @torch.library.custom_op('gnnb200::bn_act', mutates_args=())
 def bn_act(x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, relu: bool, drop_p: float,
-           seed: int, training: bool) -> Tensor:
+           seed: int, training: bool, rows_total: int = 0) -> Tensor:
     """y = drop(relu((x - mean) * invstd * gamma + beta)).  training=True means mean/invstd are the batch
-    statistics of x (the backward then includes their Jacobian); False = constants (eval mode)."""
+    statistics of x (the backward then includes their Jacobian); False = constants (eval mode).
+    rows_total > 0: x is this rank's row shard of a node-partitioned batch of rows_total rows whose
+    statistics were reduced over SYNC_GROUP; the backward all-reduces dgamma/dbeta the same way."""
     _need_cuda(x, mean, invstd, gamma, beta)
     x = _rowmajor(x)
     rows, cols = x.shape
@@ -545,23 +547,33 @@ def bn_act(x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor,
 
 
 @bn_act.register_fake
-def _(x, mean, invstd, gamma, beta, relu, drop_p, seed, training):
+def _(x, mean, invstd, gamma, beta, relu, drop_p, seed, training, rows_total=0):
     return torch.empty_like(x)
+
+
+SYNC_GROUP = None     # torch.distributed process group of the node partition (set by gnnb200.partition)
+
+
+def _bn_bwd_call(phase: int, g: Tensor, x: Tensor, mean, invstd, gamma, beta, relu, drop_p, seed, training,
+                 rows_total: int, gx: Optional[Tensor], dgamma: Tensor, dbeta: Tensor) -> None:
+    rows, cols = x.shape
+    _call_ws('gnnb200_bn_act_bwd_f32', 'bn_act_bwd', x.device, _ptr(g), _ld(g), _ptr(x), _ld(x), _ptr(mean),
+             _ptr(invstd), _ptr(gamma), _ptr(beta), int(relu), drop_p, seed, int(training), phase, rows,
+             rows_total if rows_total > 0 else rows, cols, _ptr(gx), _ld(gx) if gx is not None else 0,
+             _ptr(dgamma), _ptr(dbeta), stream=_stream(x))
 
 
 @torch.library.custom_op('gnnb200::bn_act_bwd', mutates_args=())
 def bn_act_bwd(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, relu: bool,
                drop_p: float, seed: int, training: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """Single-device backward: (grad_x, dgamma, dbeta)."""
     _need_cuda(grad_y, x, mean, invstd, gamma, beta)
     g, x = _rowmajor(grad_y), _rowmajor(x)
     rows, cols = x.shape
-    dev = x.device
-    gx = torch.empty(rows, cols, dtype=torch.float32, device=dev)
-    dgamma = torch.empty(cols, dtype=torch.float32, device=dev)
-    dbeta = torch.empty(cols, dtype=torch.float32, device=dev)
-    _call_ws('gnnb200_bn_act_bwd_f32', 'bn_act_bwd', dev, _ptr(g), _ld(g), _ptr(x), _ld(x), _ptr(mean), _ptr(invstd),
-             _ptr(gamma), _ptr(beta), int(relu), drop_p, seed, int(training), rows, cols, _ptr(gx), _ld(gx),
-             _ptr(dgamma), _ptr(dbeta), stream=_stream(x))
+    gx = torch.empty(rows, cols, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(cols, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(cols, dtype=torch.float32, device=x.device)
+    _bn_bwd_call(0, g, x, mean, invstd, gamma, beta, relu, drop_p, seed, training, 0, gx, dgamma, dbeta)
     return gx, dgamma, dbeta
 
 
@@ -570,17 +582,59 @@ def _(grad_y, x, mean, invstd, gamma, beta, relu, drop_p, seed, training):
     return torch.empty_like(x), x.new_empty(x.size(1)), x.new_empty(x.size(1))
 
 
+@torch.library.custom_op('gnnb200::bn_act_bwd_reduce', mutates_args=())
+def bn_act_bwd_reduce(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor,
+                      relu: bool, drop_p: float, seed: int) -> Tensor:
+    """Phase 1 of the partitioned backward: this shard's [2, C] = (dgamma, dbeta) partial sums."""
+    _need_cuda(grad_y, x, mean, invstd, gamma, beta)
+    g, x = _rowmajor(grad_y), _rowmajor(x)
+    out = torch.empty(2, x.size(1), dtype=torch.float32, device=x.device)
+    _bn_bwd_call(1, g, x, mean, invstd, gamma, beta, relu, drop_p, seed, True, 0, None, out[0], out[1])
+    return out
+
+
+@bn_act_bwd_reduce.register_fake
+def _(grad_y, x, mean, invstd, gamma, beta, relu, drop_p, seed):
+    return x.new_empty(2, x.size(1))
+
+
+@torch.library.custom_op('gnnb200::bn_act_bwd_apply', mutates_args=())
+def bn_act_bwd_apply(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor,
+                     dgamma_dbeta: Tensor, relu: bool, drop_p: float, seed: int, rows_total: int) -> Tensor:
+    """Phase 2: grad_x of this shard from the all-reduced (dgamma, dbeta) and the global row count."""
+    _need_cuda(grad_y, x, mean, invstd, gamma, beta, dgamma_dbeta)
+    g, x = _rowmajor(grad_y), _rowmajor(x)
+    gx = torch.empty(x.size(0), x.size(1), dtype=torch.float32, device=x.device)
+    dd = dgamma_dbeta.contiguous()
+    _bn_bwd_call(2, g, x, mean, invstd, gamma, beta, relu, drop_p, seed, True, rows_total, gx, dd[0], dd[1])
+    return gx
+
+
+@bn_act_bwd_apply.register_fake
+def _(grad_y, x, mean, invstd, gamma, beta, dgamma_dbeta, relu, drop_p, seed, rows_total):
+    return torch.empty_like(x)
+
+
 def _bn_setup(ctx, inputs, output):
-    x, mean, invstd, gamma, beta, relu, drop_p, seed, training = inputs
-    ctx.cfg = (relu, drop_p, seed, training)
+    x, mean, invstd, gamma, beta, relu, drop_p, seed, training, rows_total = inputs
+    ctx.cfg = (relu, drop_p, seed, training, rows_total)
     ctx.save_for_backward(x, mean, invstd, gamma, beta)
 
 
 def _bn_backward(ctx, gy):
     x, mean, invstd, gamma, beta = ctx.saved_tensors
-    relu, drop_p, seed, training = ctx.cfg
-    gx, dgamma, dbeta = bn_act_bwd(gy.contiguous(), x, mean, invstd, gamma, beta, relu, drop_p, seed, training)
-    return gx, None, None, dgamma, dbeta, None, None, None, None
+    relu, drop_p, seed, training, rows_total = ctx.cfg
+    gy = gy.contiguous()
+    if rows_total > 0 and training and SYNC_GROUP is not None:
+        import torch.distributed as dist
+        local = bn_act_bwd_reduce(gy, x, mean, invstd, gamma, beta, relu, drop_p, seed)
+        total = local.clone()
+        dist.all_reduce(total, group=SYNC_GROUP)
+        gx = bn_act_bwd_apply(gy, x, mean, invstd, gamma, beta, total, relu, drop_p, seed, rows_total)
+        # parameter gradients stay per-shard partial sums: the flat gradient all-reduce adds them up
+        return gx, None, None, local[0], local[1], None, None, None, None, None
+    gx, dgamma, dbeta = bn_act_bwd(gy, x, mean, invstd, gamma, beta, relu, drop_p, seed, training)
+    return gx, None, None, dgamma, dbeta, None, None, None, None, None
 
 
 bn_act.register_autograd(_bn_backward, setup_context=_bn_setup)

@@ -155,6 +155,9 @@ int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols
  *   bwd     : recomputes x_hat / ReLU sign / dropout mask from x (the saved pre-BN activation);
  *             writes grad_x, dgamma, dbeta (two-stage fixed-order column reductions).
  *             training = 0 treats mean/invstd as constants (eval mode).
+ *             phase 0 = reduce + apply on one device; phase 1 = reduce only (local dgamma/dbeta);
+ *             phase 2 = apply only with caller-provided (all-reduced) dgamma/dbeta and the global
+ *             row count rows_total — the node-partitioned multi-GPU path.
  * cols % 4 == 0 and 16-byte aligned rows are required (GNNB200_EUNSUPPORTED otherwise).
  * ------------------------------------------------------------------------------------------ */
 int gnnb200_bn_finalize_f32(const float* sum, const float* m2, int64_t rows, int64_t cols, float eps,
@@ -165,9 +168,9 @@ int gnnb200_bn_act_fwd_f32(const float* x, int64_t ldx, const float* mean, const
                            int64_t rows, int64_t cols, float* y, int64_t ldy, gnnb200_stream_t stream);
 int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const float* x, int64_t ldx, const float* mean,
                            const float* invstd, const float* gamma, const float* beta, int relu, float drop_p,
-                           uint64_t seed, int training, int64_t rows, int64_t cols, float* grad_x, int64_t ldgx,
-                           float* dgamma, float* dbeta, void* workspace, size_t* workspace_bytes,
-                           gnnb200_stream_t stream);
+                           uint64_t seed, int training, int phase, int64_t rows, int64_t rows_total, int64_t cols,
+                           float* grad_x, int64_t ldgx, float* dgamma, float* dbeta, void* workspace,
+                           size_t* workspace_bytes, gnnb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Link-prediction decoder input (K8, src/models/heads.py:59-65): for each edge (u,v)

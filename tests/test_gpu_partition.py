@@ -1,0 +1,106 @@
+"""The node-partitioned path with the real kernels: world size 1 equals the single-device path bit for
+bit; world size 2 over NCCL (needs 2 GPUs, skipped otherwise) reproduces the single-device activations
+and gradients of the same graph."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gnnb200  # noqa: F401
+from gnnb200 import models as prod
+from gnnb200 import partition, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _single(dev, data, n, layers, seed=0):
+    torch.manual_seed(seed)
+    model = torch.nn.ModuleDict({'input_encoder': prod.InputEncoder(100, 256), 'gnn_backbone': prod.GINBackbone(layers, 256)}).to(dev)
+    model.train()
+    old = prod.DROPOUT_RATE
+    prod.DROPOUT_RATE = 0.0
+    model['input_encoder'].dropout.p = 0.0
+    try:
+        h = model['gnn_backbone'](model['input_encoder'](data['x']), data['edge_index'])
+        w = torch.randn(h.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        (h * w).sum().backward()
+    finally:
+        prod.DROPOUT_RATE = old
+    return h.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}, w
+
+
+def test_world1_partition_equals_single_device():
+    dev = torch.device('cuda')
+    n, e = 5000, 60000
+    data = synthetic.products_like(n, e, 100, seed=1, device=dev)
+    torch.manual_seed(0)
+    step = partition.PartitionedBackboneStep(prod, dev, 100, 256, 3, n, 0, 1, seed=0)
+    torch.manual_seed(5)
+    l1 = step.step(data['x'], data['edge_index'])
+    torch.manual_seed(0)
+    model = torch.nn.ModuleDict({'input_encoder': prod.InputEncoder(100, 256), 'gnn_backbone': prod.GINBackbone(3, 256)}).to(dev)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    torch.manual_seed(5)
+    opt.zero_grad(set_to_none=True)
+    h = model['gnn_backbone'](model['input_encoder'](data['x']), data['edge_index'])
+    l2 = h.sum()
+    l2.backward()
+    opt.step()
+    assert torch.equal(l1, l2)
+    for (ka, pa), (kb, pb) in zip(step.model.named_parameters(), model.named_parameters()):
+        assert torch.equal(pa, pb), ka
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        n, e, layers = 6001, 80000, 3
+        data = synthetic.products_like(n, e, 100, seed=2, device=dev)
+        h_ref, g_ref, w = _single(dev, data, n, layers)
+        torch.manual_seed(0)
+        model = torch.nn.ModuleDict({'input_encoder': prod.InputEncoder(100, 256), 'gnn_backbone': prod.GINBackbone(layers, 256)}).to(dev)
+        model.train()
+        model['input_encoder'].dropout.p = 0.0
+        old = prod.DROPOUT_RATE
+        prod.DROPOUT_RATE = 0.0
+        graph = partition.PartitionedGraph(data['edge_index'], n, rank, world)
+        with partition.partition_scope(graph):
+            h = model['gnn_backbone'](model['input_encoder'](data['x'][graph.lo:graph.hi]), graph)
+            (h * w[graph.lo:graph.hi]).sum().backward()
+        prod.DROPOUT_RATE = old
+        partition.allreduce_gradients(model)
+        act = float((h.detach() - h_ref[graph.lo:graph.hi]).abs().max() / h_ref.abs().max())
+        assert act < 2e-3, act                      # tf32 GEMMs + different BN merge order
+        for k, p in model.named_parameters():
+            ref = g_ref[k]
+            if float(ref.abs().max()) < 1e-6:
+                continue
+            fro = float((p.grad - ref).norm() / ref.norm())
+            assert fro < 5e-2, (k, fro)
+        # running statistics are global, identical on every rank
+        rm = model['gnn_backbone'].layers[0].batch_norm.running_mean.clone()
+        both = [torch.empty_like(rm) for _ in range(world)]
+        dist.all_gather(both, rm)
+        assert torch.equal(both[0], both[1])
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_world2_nccl_matches_single_device(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(2))

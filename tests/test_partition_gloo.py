@@ -1,0 +1,109 @@
+"""Host-side logic of the node-partitioned multi-GPU path (gnnb200/partition.py) on CPU with the gloo
+backend, world size 2: shard bounds, padded all-gather of row shards, the partition algebra of the
+aggregation forward and its transposed backward (the CUDA gather is stood in for by the oracle's CPU
+scatter — only the decomposition + collectives are under test here), Chan merge of BatchNorm moments,
+and the flat gradient all-reduce.  The real kernels over NCCL are covered by tests/test_gpu_partition.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gnnb200  # noqa: F401
+from gnnb200 import partition
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _oracle_agg(x_full, rowptr, col, self_x, eps):
+    """CPU stand-in for gnnb200_aggregate_f32 (sequential edge-order sums over a CSR)."""
+    n = rowptr.numel() - 1
+    out = torch.zeros(n, x_full.size(1))
+    deg = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n), deg)
+    out.index_add_(0, rows, x_full[col.long()])
+    return out + (1 + eps) * self_x
+
+
+def _csr(keys, others, n):
+    perm = torch.sort(keys, stable=True).indices
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(keys, minlength=n).cumsum(0)])
+    return rowptr, others[perm]
+
+
+def _worker(rank, world, port, n, e, f, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        ei = torch.randint(0, n, (2, e), generator=g)
+        x = torch.randn(n, f, generator=g)
+        gout = torch.randn(n, f, generator=g)
+        eps = torch.tensor([0.3])
+        lo, hi, per = partition.shard_bounds(n, rank, world)
+
+        # ---- single-graph answer (every rank computes it for comparison) ----
+        xr = x.clone().requires_grad_(True)
+        z = torch.zeros(n, f).index_add_(0, ei[1], xr[ei[0]]) + (1 + eps) * xr
+        z.backward(gout)
+
+        # ---- partitioned: forward over own dst rows, backward over own src rows ----
+        shell = partition.PartitionedGraph.__new__(partition.PartitionedGraph)
+        shell.num_nodes, shell.rank, shell.world, shell.group = n, rank, world, None
+        shell.lo, shell.hi, shell.per, shell.n_local = lo, hi, per, hi - lo
+        own_dst = (ei[1] >= lo) & (ei[1] < hi)
+        rp, col = _csr(ei[1][own_dst] - lo, ei[0][own_dst], hi - lo)
+        own_src = (ei[0] >= lo) & (ei[0] < hi)
+        rpt, colt = _csr(ei[0][own_src] - lo, ei[1][own_src], hi - lo)
+        h_full = shell.all_gather_rows(x[lo:hi])
+        assert torch.equal(h_full, x)
+        z_loc = _oracle_agg(h_full, rp, col, x[lo:hi], eps)
+        torch.testing.assert_close(z_loc, z.detach()[lo:hi], rtol=1e-6, atol=1e-6)
+        g_full = shell.all_gather_rows(gout[lo:hi])
+        assert torch.equal(g_full, gout)
+        gh_loc = _oracle_agg(g_full, rpt, colt, gout[lo:hi], eps)
+        torch.testing.assert_close(gh_loc, xr.grad[lo:hi], rtol=1e-5, atol=1e-5)
+
+        # ---- BatchNorm moments: Chan merge over ranks == moments of the whole activation ----
+        a = torch.randn(n, 8, generator=g) * 3 + 10
+        loc = a[lo:hi]
+        s, m2 = loc.sum(0), ((loc - loc.mean(0)) ** 2).sum(0)
+        tn, ts, tm2 = partition.merge_moments(partition.gather_moments(hi - lo, s, m2, None))
+        assert torch.equal(tn, torch.full((8,), float(n)))
+        torch.testing.assert_close(ts / tn, a.mean(0), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(tm2 / tn, a.var(0, unbiased=False), rtol=1e-4, atol=1e-5)
+
+        # ---- flat gradient all-reduce ----
+        lin = torch.nn.Linear(4, 3)
+        with torch.no_grad():
+            for p in lin.parameters():
+                p.fill_(1.0)
+        lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+        lin.bias.grad = torch.full_like(lin.bias, 10.0 * (rank + 1))
+        partition.allreduce_gradients(lin)
+        assert torch.equal(lin.weight.grad, torch.full_like(lin.weight, float(sum(range(1, world + 1)))))
+        assert torch.equal(lin.bias.grad, torch.full_like(lin.bias, 10.0 * sum(range(1, world + 1))))
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n,e', [(101, 700), (64, 300)])
+def test_partition_algebra_world2(tmp_path, n, e):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n, e, 16, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+def test_shard_bounds_cover_everything():
+    for n in (1, 7, 100, 2_449_029):
+        for world in (1, 2, 4, 8):
+            spans = [partition.shard_bounds(n, r, world)[:2] for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
