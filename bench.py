@@ -258,7 +258,7 @@ def run_product(args):
                     'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches,
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30,
-            'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM> (fwd and transposed bwd)',
+            'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM,2,6> (fwd and transposed bwd)',
                          'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / pk['hbm_gbs'] if achieved else None, 'traffic': traffic,
                          'peak_source': pk['source'], 'launches_timed': len(agg_ms),

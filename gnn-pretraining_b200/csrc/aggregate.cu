@@ -2,20 +2,20 @@
 // Replaces PyG GINConv.propagate's index_select + scatter_add_ and the (1+eps)*x self term
 // (reference src/models/gnn.py:29-37,41).  HBM-bound gather: G lanes own one destination row,
 // each lane keeps V float4 accumulators (row width F <= G*V*4), neighbour rows are streamed with
-// 128-bit no-allocate loads U at a time so several KB per warp are in flight, and the adds are
+// 128-bit no-allocate loads U rows at a time at high occupancy (register-capped), and the adds are
 // applied strictly in edge order from 0.0f -> bit-identical to the CPU scatter_add_ order, no
 // float atomics.  The backward pass is the same kernel on the by-src CSR.
 #include "common.cuh"
 
 namespace gnnb200 {
 
-template <int G, int V, int MODE>
-__global__ void __launch_bounds__(256)
+template <int G, int V, int MODE, int U = 4, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 aggregate_vec_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ col, int64_t num_rows, int feat,
                      const float* __restrict__ self_x, int64_t lds, const float* __restrict__ eps_ptr,
                      const float* __restrict__ dinv, float* __restrict__ out, int64_t ldo) {
-  constexpr int U = 4;  // neighbour rows in flight per group
+  // U = neighbour rows in flight per group
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);                 // lane inside the row group
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
@@ -119,15 +119,20 @@ static int launch_vec(int mode, const float* x, int64_t ldx, const int32_t* rowp
   const int block = 256;
   const int64_t threads = num_rows * G;
   const unsigned grid = (unsigned)((threads + block - 1) / block);
+  // Occupancy beats per-warp memory-level parallelism for this gather (measured on B200 at C5 scale, F = 256:
+  // U=4 / 91 registers -> 16.2 ms per pass, U=2 capped at 40 registers (6 CTAs/SM) -> 10.5 ms = the measured
+  // HBM copy peak), so the register cap grows only with the accumulator count V.
+  constexpr int U = (V >= 8) ? 1 : 2;
+  constexpr int MINB = (V <= 2) ? 6 : ((V == 4) ? 3 : 2);
   switch (mode) {
     case GNNB200_AGG_SUM:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_SUM><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
+      aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
       break;
     case GNNB200_AGG_MEAN:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_MEAN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
+      aggregate_vec_kernel<G, V, GNNB200_AGG_MEAN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
       break;
     default:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_GCN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
+      aggregate_vec_kernel<G, V, GNNB200_AGG_GCN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
       break;
   }
   GNNB200_LAUNCH_CHECK();
@@ -177,6 +182,41 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
       aggregate_scalar_kernel<GNNB200_AGG_GCN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo);
       break;
   }
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+
+// Development-only tuning hook (not part of include/gnnb200.h): SUM mode, F = 256, 16-byte aligned.
+extern "C" int gnnb200_dev_aggregate_variant(const float* x, const int32_t* rowptr, const int32_t* col, int64_t num_rows,
+                                             const float* eps, float* out, int variant, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int feat = 256;
+  const int64_t ld = 256;
+#define GNNB200_VARIANT(G, V, U, MINB)                                                                              \
+  {                                                                                                                  \
+    const unsigned grid = (unsigned)((num_rows * G + 255) / 256);                                                    \
+    aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, 256, 0, stream>>>(x, ld, rowptr, col, num_rows, feat, \
+                                                                                   x, ld, eps, nullptr, out, ld);    \
+  }
+  switch (variant) {
+    case 0: GNNB200_VARIANT(32, 2, 4, 1) break;
+    case 1: GNNB200_VARIANT(32, 2, 4, 4) break;
+    case 2: GNNB200_VARIANT(32, 2, 8, 2) break;
+    case 3: GNNB200_VARIANT(32, 2, 2, 6) break;
+    case 4: GNNB200_VARIANT(16, 4, 4, 2) break;
+    case 5: GNNB200_VARIANT(16, 4, 2, 4) break;
+    case 6: GNNB200_VARIANT(32, 2, 8, 3) break;
+    case 7: GNNB200_VARIANT(32, 2, 2, 4) break;
+    case 8: GNNB200_VARIANT(32, 2, 2, 8) break;
+    case 9: GNNB200_VARIANT(32, 2, 1, 8) break;
+    case 10: GNNB200_VARIANT(32, 2, 3, 6) break;
+    case 11: GNNB200_VARIANT(32, 2, 2, 5) break;
+    case 12: GNNB200_VARIANT(32, 2, 1, 6) break;
+    case 13: GNNB200_VARIANT(32, 2, 3, 5) break;
+    default: return GNNB200_EINVAL;
+  }
+#undef GNNB200_VARIANT
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
