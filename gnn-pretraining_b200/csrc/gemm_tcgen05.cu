@@ -8,18 +8,20 @@
 //   A "K-major"  : stored [M,K] row-major (transa=0)      A "MN-major": stored [K,M] (transa=1)
 //   B "K-major"  : stored [N,K] row-major (transb=1)      B "MN-major": stored [K,N] (transb=0)
 //
-// Persistent kernel, one CTA per SM, 256 threads:
+// Persistent kernel, one CTA per SM, 384 threads:
 //   warp 0   TMA producer (one elected lane): kStages-deep ring of {A tile 128x32, B tile BNx32} fp32
 //   warp 1   MMA issuer  (one elected lane): 4 x tcgen05.mma (M=128, N=BN, K=8) per stage,
 //            tcgen05.commit releases the stage; accumulators double-buffered in TMEM (2 x BN columns)
 //   warp 2   TMEM allocator (512 columns)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/ReLU -> 128-bit global stores,
-//            overlapped with the next tile's main loop
+//   warps 4-11 epilogue (two per TMEM lane quarter, each half of the columns): tcgen05.ld 32 lanes x 32
+//            columns (next chunk prefetched) -> smem transpose -> bias/residual/ReLU -> coalesced 128-bit
+//            global stores, overlapped with the next tile's main loop
 // Split-K (used for the weight gradients, K = number of nodes): each (tile, split) writes an fp32
 // partial to the workspace, a second kernel sums the splits in order (deterministic) and applies the
 // epilogue.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the store.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gnnb200 {
@@ -29,9 +31,11 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // fp32 elements per stage along K = one 128-byte swizzle span
 constexpr int UMMA_K = 8;        // kind::tf32
-constexpr int kStages = 4;
-constexpr int kThreads = 256;
+constexpr int kStages = 3;        // 3 x 48 KB operand stages + 8 epilogue transpose tiles fit the 227 KB of one SM
+constexpr int kThreads = 384;     // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kTmemCols = 512;
+constexpr int kEpiPitch = 36;      // floats per row of the epilogue transpose tile (16 B aligned, conflict-free)
 constexpr uint32_t kSpinLimit = 1u << 27;   // bounded mbarrier spin: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,6 +135,7 @@ struct Params {
   const float* residual;  // [M,N] added in the epilogue (GINLayer's `+ h`), only when splits == 1
   long long ldr;
   int relu;
+  int debug;          // dev only (env GNNB200_GEMM_DEBUG): 1 = skip epilogue global stores, 2 = skip the whole epilogue body
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -144,6 +149,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
+  float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes);                       // kEpiWarps x 32 x kEpiPitch
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
@@ -163,7 +169,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -256,8 +262,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..7 <-> TMEM lanes 0..127) =====================
+    // ===================== epilogue (warps 4..11) =====================
+    // A warp may only touch TMEM lanes 32*(warp%4)..+31; two warps share each lane quarter and split the
+    // accumulator's columns, so every SM sub-partition has two epilogue warps to interleave.
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunksPerWarp = BN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -265,46 +275,72 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tile_coords(t, m0, n0, kb0, kb1, split);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m0 + q * 32 + lane;
-      float* crow = p.C + (p.splits > 1 ? (long long)split * p.M * p.N : 0) + (long long)row * p.ldc + n0;
+      float* cbase = p.C + (p.splits > 1 ? (long long)split * p.M * p.N : 0);
       const bool has_k = kb1 > kb0;                    // an empty split contributes zeros
+      // TMEM gives lane = row; a direct store would touch 32 rows x 16 B per instruction.  Each warp instead
+      // transposes its 32x32 chunk through a private smem tile (pitch 36 floats: conflict-free 128-bit
+      // stores by row and 128-bit loads by quarter-warp) and writes 4 full 128-byte row segments per
+      // instruction; bias / residual / ReLU are applied on the coalesced side.
+      float* stage = epi_smem + (warp - 4) * (32 * kEpiPitch);
+      const int r_in = lane >> 3;                      // row inside a group of 4
+      const int c4 = (lane & 7) << 2;                  // column (floats) inside the 32-wide chunk
+      const int c_begin = half * kChunksPerWarp, c_end = c_begin + kChunksPerWarp;
+      uint32_t v[32];
+      if (p.debug != 2) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_begin * 32), v);
+      } else {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_wait();
-        if (row < p.M) {
+      for (int c = c_begin; c < (p.debug == 2 ? c_begin : c_end); ++c) {
+        const int col = n0 + c * 32 + c4;
+        // residual rows for this chunk are requested first so their latency hides behind the TMEM load and the
+        // transpose (8 independent 128-bit loads per lane, coalesced: 4 full 128-byte segments per instruction)
+        float4 rr[8];
+        if (p.splits == 1 && p.residual) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int col = n0 + c * 32 + j;
-            if (col < p.N) {                            // N % 4 == 0 is guaranteed by the host
-              float4 o;
-              o.x = has_k ? __uint_as_float(v[j + 0]) : 0.f;
-              o.y = has_k ? __uint_as_float(v[j + 1]) : 0.f;
-              o.z = has_k ? __uint_as_float(v[j + 2]) : 0.f;
-              o.w = has_k ? __uint_as_float(v[j + 3]) : 0.f;
-              if (p.splits == 1) {
-                if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                if (p.residual) {
-                  const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col));
-                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
-                if (p.relu) {
-                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                }
-              }
-              *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
-            }
+          for (int it = 0; it < 8; ++it) {
+            const int row = m0 + q * 32 + it * 4 + r_in;
+            rr[it] = (row < p.M && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * kEpiPitch + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        if (c + 1 < c_end) {                           // next chunk's TMEM load overlaps this chunk's stores
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + (c + 1) * 32), v);
+        } else {                                       // accumulator fully read: hand TMEM back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        __syncwarp();
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.splits == 1 && p.bias && col < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + r_in;
+          const int row = m0 + q * 32 + r;
+          float4 o = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + c4);
+          if (row < p.M && col < p.N) {                 // N % 4 == 0 is guaranteed by the host
+            if (!has_k) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.splits == 1) {
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              if (p.residual) { o.x += rr[it].x; o.y += rr[it].y; o.z += rr[it].z; o.w += rr[it].w; }
+              if (p.relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+            }
+            if (p.debug != 1) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+          }
+        }
+        __syncwarp();                                   // the staging tile is reused by the next chunk
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -401,7 +437,7 @@ static int pick_bn(long long N) {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kStages * (BM * BK * 4 + BN * BK * 4) + 1024;
+  constexpr size_t smem = (size_t)kStages * (BM * BK * 4 + BN * BK * 4) + kEpiWarps * 32 * kEpiPitch * 4 + 1024;
   static bool configured = false;
   if (!configured) {
     GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -483,6 +519,10 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   p.residual = splits > 1 ? nullptr : residual;
   p.ldr = ldr;
   p.relu = (splits == 1 && (epilogue & GNNB200_EPI_RELU)) ? 1 : 0;
+  {
+    const char* dbg = getenv("GNNB200_GEMM_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const long long total = tiles * splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
   if (bn == 256) rc = launch_bn<256>(a_mn, b_mn, ma, mb, p, grid, stream);
