@@ -286,9 +286,111 @@ def run_product(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(args, budget_steps=1)
+        if world == 1 and args.secondary:
+            sec = small_graph_steps('gnnb200', dev, steps=40, warmup=6)
+            if not args.no_cpu_baseline:
+                torch.set_num_threads(os.cpu_count() or 1)
+                cpu = small_graph_steps('oracle', torch.device('cpu'), steps=4, warmup=1)
+                sec['cpu_oracle'] = {k: v for k, v in cpu.items() if k.endswith('_per_s')}
+                sec['cpu_oracle']['cores'] = torch.get_num_threads()
+            out['secondary'] = sec
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary workloads: BASELINE configs[1] (ENZYMES-shaped fine-tune step) and configs[2] (s4 pre-training step)
+# ------------------------------------------------------------------------------------------------
+S4_TASKS = ['node_feat_mask', 'link_pred', 'node_contrast', 'graph_contrast', 'graph_prop']
+S4_DOMAINS = ['Cora_NC', 'CiteSeer_NC', 'ENZYMES']
+
+
+def _graph_lists():
+    from gnnb200 import synthetic
+    return {'c2': synthetic.tu_like_graphs('ENZYMES', 128, seed=42),
+            'Cora_NC': [dict(synthetic.cora_like(42), graph_properties=torch.zeros(12))],
+            'CiteSeer_NC': [dict(synthetic.citeseer_like(43), graph_properties=torch.zeros(12))],
+            'ENZYMES': synthetic.tu_like_graphs('ENZYMES', 32, seed=44)}
+
+
+def _make_batch(data_mod, graphs, device):
+    b = data_mod.Batch.from_data_list([data_mod.Data(**{k: v.clone() for k, v in g.items()}) for g in graphs])
+    return b.to(device)
+
+
+def small_graph_steps(impl, device, steps, warmup):
+    """(fine-tune steps/s on C2, s4 pre-training steps/s on C3) for `impl` in {'gnnb200', 'oracle'}.
+    The s4 step = the 5 task losses of scheme s4 (src/pretrain/pretrain.py:50) on three domains + one backward
+    sweep per task (what gradient surgery drives, src/pretrain/gradient_surgery.py:18-21) + AdamW; the
+    PCGrad projection itself is host-side code outside the hot path."""
+    import random
+    if impl == 'gnnb200':
+        from gnnb200 import data as data_mod, models, tasks as task_mod
+    else:
+        from oracle import modules as models
+        from oracle import install_pyg_shim
+        install_pyg_shim()
+        import torch_geometric.data as data_mod
+        task_mod = models
+    sync = (lambda: torch.cuda.synchronize()) if device.type == 'cuda' else (lambda: None)
+    lists = _graph_lists()
+    out = {}
+    # ---- C2: graph-classification fine-tune step ----
+    torch.manual_seed(0)
+    ft = models.FinetuneGNN(device, 'ENZYMES', 'full_finetune')
+    ft.train()
+    opt = torch.optim.AdamW(ft.param_groups)
+    batch = _make_batch(data_mod, lists['c2'], device)
+
+    def ft_step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(ft(batch), batch.y)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(warmup):
+        ft_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ft_step()
+    sync()
+    out['c2_finetune_steps_per_s'] = steps / (time.perf_counter() - t0)
+    out['c2_shape'] = {'graphs': 128, 'nodes': int(batch.x.size(0)), 'edges': int(batch.edge_index.size(1))}
+    # ---- C3: s4 multi-task pre-training step ----
+    torch.manual_seed(0)
+    pm = models.PretrainableGNN(device, S4_DOMAINS, S4_TASKS)
+    pm.train()
+    popt = torch.optim.AdamW(pm.parameters(), lr=1e-4)
+    temp, grl = task_mod.TemperatureScheduler(1000), task_mod.GRLScheduler(50, 100)
+    tasks = task_mod.instantiate_tasks(pm, S4_TASKS, grl, temp)
+    batches = {d: _make_batch(data_mod, lists[d], device) for d in S4_DOMAINS}
+    gen = torch.Generator().manual_seed(42)
+    random.seed(42)
+
+    def s4_step():
+        popt.zero_grad(set_to_none=True)
+        total = 0.0
+        for name, task in tasks.items():
+            loss, _ = task.compute_loss(batches, gen)
+            loss.backward()
+            total = total + loss.detach()
+        torch.nn.utils.clip_grad_norm_(pm.parameters(), max_norm=0.5)
+        popt.step()
+        temp.step()
+        return total
+    s4_steps = max(2, steps // 4)
+    for _ in range(max(1, warmup // 2)):
+        s4_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(s4_steps):
+        s4_step()
+    sync()
+    out['c3_s4_pretrain_steps_per_s'] = s4_steps / (time.perf_counter() - t0)
+    out['c3_shape'] = {'domains': S4_DOMAINS, 'tasks': S4_TASKS, 'backbone_passes_per_step': 21}
     return out
 
 
@@ -358,7 +460,18 @@ def main():
     ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
+    ap.add_argument('--secondary', action='store_true', help='also time the small-graph configs (C2 fine-tune step, C3 s4 step)')
+    ap.add_argument('--only-secondary', action='store_true', help='time only the small-graph configs and print them')
     args = ap.parse_args()
+    if args.only_secondary:
+        import gnnb200  # noqa: F401
+        dev = torch.device('cuda', 0)
+        sec = small_graph_steps('gnnb200', dev, steps=40, warmup=6)
+        if not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sec['cpu_oracle'] = small_graph_steps('oracle', torch.device('cpu'), steps=4, warmup=1)
+        print(json.dumps(sec), flush=True)
+        return
     if args.impl == 'reference':
         out = run_reference(args)
     else:

@@ -102,9 +102,84 @@ def _call_ws(name: str, what: str, device, *args, stream: int):
 
 
 # ---------------------------------------------------------------------------------------------
+# registration: every op is defined in the torch.library namespace ``gnnb200`` (schema inferred from the
+# annotations, CUDA implementation only -> CPU tensors raise, fake/meta kernel, autograd formula), so
+# ``torch.ops.gnnb200.<name>`` is the public operator surface.  The modules of this package call the same
+# Python implementation through a thin fast path (direct call, or one torch.autograd.Function when a
+# gradient is needed): the dispatcher round trip of a Python custom op costs ~60-80 us per call, which is
+# what bounds the small-graph configs (hundreds of ops per step), not the kernels.
+# ---------------------------------------------------------------------------------------------
+import inspect
+
+_LIBRARY = torch.library.Library('gnnb200', 'DEF')
+
+
+class _Op:
+    def __init__(self, name: str, fn, mutates):
+        self.name, self.fn, self.qualname = name, fn, f'gnnb200::{name}'
+        self.__doc__ = fn.__doc__
+        schema = torch.library.infer_schema(fn, mutates_args=mutates)
+        _LIBRARY.define(name + schema)
+        _LIBRARY.impl(name, fn, 'CUDA')
+        sig = inspect.signature(fn)
+        self._params = list(sig.parameters.values())
+        self._names = [p.name for p in self._params]
+        self._autograd = None
+
+    def register_fake(self, fake):
+        torch.library.register_fake(self.qualname)(fake)
+        return fake
+
+    def register_autograd(self, backward, setup_context):
+        torch.library.register_autograd(self.qualname, backward, setup_context=setup_context)
+        impl = self.fn
+
+        class _Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *args):
+                out = impl(*args)
+                setup_context(ctx, args, out)
+                return out
+
+            @staticmethod
+            def backward(ctx, *grads):
+                return backward(ctx, *grads)
+
+        _Fn.__name__ = f'gnnb200_{self.name}'
+        self._autograd = _Fn
+
+    def _bind(self, args, kwargs):
+        if not kwargs and len(args) == len(self._params):
+            return args
+        full = list(args)
+        for p in self._params[len(args):]:
+            if p.name in kwargs:
+                full.append(kwargs[p.name])
+            elif p.default is not inspect.Parameter.empty:
+                full.append(p.default)
+            else:
+                raise TypeError(f'{self.qualname}: missing argument {p.name!r}')
+        return tuple(full)
+
+    def __call__(self, *args, **kwargs):
+        args = self._bind(args, kwargs)
+        if self._autograd is not None and torch.is_grad_enabled():
+            for a in args:
+                if isinstance(a, Tensor) and a.requires_grad:
+                    return self._autograd.apply(*args)
+        return self.fn(*args)
+
+
+def _op(name: str, mutates=()):
+    def wrap(fn):
+        return _Op(name, fn, mutates)
+    return wrap
+
+
+# ---------------------------------------------------------------------------------------------
 # structure ops (integer, bit-exact)
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('gnnb200::csr_build', mutates_args=())
+@_op('csr_build')
 def csr_build(edge_index: Tensor, num_nodes: int, by_src: bool) -> Tuple[Tensor, Tensor, Tensor]:
     """(rowptr int32 [N+1], col int32 [E], eid int32 [E]); see gnnb200_csr_build_i64."""
     _need_cuda(edge_index)
@@ -128,7 +203,7 @@ def _(edge_index, num_nodes, by_src):
     return mk(num_nodes + 1), mk(E), mk(E)
 
 
-@torch.library.custom_op('gnnb200::segment_ptr', mutates_args=())
+@_op('segment_ptr')
 def segment_ptr(ids: Tensor, num_segments: int) -> Tensor:
     """Offsets int32 [S+1] of a sorted int64 id vector (Batch.batch -> ptr)."""
     _need_cuda(ids)
@@ -144,7 +219,7 @@ def _(ids, num_segments):
     return ids.new_empty(num_segments + 1, dtype=torch.int32)
 
 
-@torch.library.custom_op('gnnb200::coalesce', mutates_args=())
+@_op('coalesce')
 def coalesce(edge_index: Tensor, num_nodes: int) -> Tuple[Tensor, Tensor]:
     """(out [2, E] capacity buffer, count int64 [1]): columns sorted by row*N+col, duplicates dropped."""
     _need_cuda(edge_index)
@@ -187,7 +262,7 @@ def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Op
     return out
 
 
-@torch.library.custom_op('gnnb200::aggregate', mutates_args=())
+@_op('aggregate')
 def aggregate(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Optional[Tensor] = None,
               eps: Optional[Tensor] = None, dinv: Optional[Tensor] = None) -> Tensor:
     """Raw CSR aggregation (no autograd): see gnnb200_aggregate_f32."""
@@ -199,7 +274,7 @@ def _(x, rowptr, col, mode, self_x=None, eps=None, dinv=None):
     return x.new_empty(rowptr.numel() - 1, x.size(1))
 
 
-@torch.library.custom_op('gnnb200::dot', mutates_args=())
+@_op('dot')
 def dot(a: Tensor, b: Tensor) -> Tensor:
     """Deterministic sum(a*b) -> [1]."""
     _need_cuda(a, b)
@@ -214,7 +289,7 @@ def _(a, b):
     return a.new_empty(1)
 
 
-@torch.library.custom_op('gnnb200::gin_aggregate', mutates_args=())
+@_op('gin_aggregate')
 def gin_aggregate(x: Tensor, eps: Tensor, rowptr: Tensor, col: Tensor, rowptr_t: Tensor, col_t: Tensor) -> Tensor:
     """z[i] = sum_{e: dst=i} x[src_e] + (1+eps) * x[i]   (GINConv before its MLP).
     rowptr/col: CSR grouped by dst; rowptr_t/col_t: grouped by src (used by the backward)."""
@@ -250,7 +325,7 @@ gin_aggregate.register_autograd(_gin_backward, setup_context=_gin_setup)
 # ---------------------------------------------------------------------------------------------
 # pooling
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('gnnb200::segment_pool', mutates_args=())
+@_op('segment_pool')
 def segment_pool(x: Tensor, ptr: Tensor, mode: int) -> Tensor:
     """Segment sum/mean/max over row ranges ptr (int32 [S+1]) -> [S, F]."""
     _need_cuda(x, ptr)
@@ -267,7 +342,7 @@ def _(x, ptr, mode):
     return x.new_empty(ptr.numel() - 1, x.size(1))
 
 
-@torch.library.custom_op('gnnb200::segment_pool_bwd', mutates_args=())
+@_op('segment_pool_bwd')
 def segment_pool_bwd(grad_out: Tensor, x: Tensor, out: Tensor, ptr: Tensor, mode: int) -> Tensor:
     _need_cuda(grad_out, x, out, ptr)
     g, x, out = _rowmajor(grad_out), _rowmajor(x), _rowmajor(out)
@@ -301,7 +376,7 @@ segment_pool.register_autograd(_pool_backward, setup_context=_pool_setup)
 # ---------------------------------------------------------------------------------------------
 # row gather / scatter
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('gnnb200::rows_gather', mutates_args=())
+@_op('rows_gather')
 def rows_gather(x: Tensor, idx: Tensor) -> Tensor:
     """out[i] = x[idx[i]] (idx int64)."""
     _need_cuda(x, idx)
@@ -318,7 +393,7 @@ def _(x, idx):
     return x.new_empty(idx.numel(), x.size(1))
 
 
-@torch.library.custom_op('gnnb200::rows_gather_bwd', mutates_args=())
+@_op('rows_gather_bwd')
 def rows_gather_bwd(grad_out: Tensor, idx: Tensor, num_rows: int) -> Tensor:
     """Deterministic transpose of rows_gather: grad_x[r] = sum_{i: idx[i]==r} grad_out[i]."""
     _need_cuda(grad_out, idx)
@@ -350,7 +425,7 @@ def _rg_backward(ctx, g):
 rows_gather.register_autograd(_rg_backward, setup_context=_rg_setup)
 
 
-@torch.library.custom_op('gnnb200::rows_scatter', mutates_args=())
+@_op('rows_scatter')
 def rows_scatter(base: Tensor, src: Tensor, idx: Tensor) -> Tensor:
     """Copy of ``base`` with rows idx[i] replaced by src[i] (src [M,F]) or by the single row src [F]."""
     _need_cuda(base, src, idx)
@@ -416,7 +491,7 @@ def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[T
     return c
 
 
-@torch.library.custom_op('gnnb200::gemm', mutates_args=())
+@_op('gemm')
 def gemm(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor] = None, relu: bool = False,
          precision: int = 0) -> Tensor:
     """C = op(a) op(b) (+bias)(ReLU), raw (no autograd): see gnnb200_gemm_f32."""
@@ -430,7 +505,7 @@ def _(a, transa, b, transb, bias=None, relu=False, precision=0):
     return a.new_empty(M, N)
 
 
-@torch.library.custom_op('gnnb200::colsum', mutates_args=())
+@_op('colsum')
 def colsum(x: Tensor) -> Tensor:
     """Deterministic per-column sum [F] (bias gradients)."""
     _need_cuda(x)
@@ -446,7 +521,7 @@ def _(x):
     return x.new_empty(x.size(1))
 
 
-@torch.library.custom_op('gnnb200::colstats', mutates_args=())
+@_op('colstats')
 def colstats(x: Tensor) -> Tuple[Tensor, Tensor]:
     """(sum [F], centred second moment [F]) per column: BatchNorm batch statistics."""
     _need_cuda(x)
@@ -463,7 +538,7 @@ def _(x):
     return x.new_empty(x.size(1)), x.new_empty(x.size(1))
 
 
-@torch.library.custom_op('gnnb200::linear', mutates_args=())
+@_op('linear')
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int,
            residual: Optional[Tensor] = None) -> Tensor:
     """y = x W^T + b (+ residual) with W [out, in] (nn.Linear layout); the residual add (GINLayer's
@@ -504,7 +579,7 @@ linear.register_autograd(_lin_backward, setup_context=_lin_setup)
 # ---------------------------------------------------------------------------------------------
 # fused BatchNorm1d (+ReLU)(+dropout)
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('gnnb200::bn_batch_stats', mutates_args=('running_mean', 'running_var'))
+@_op('bn_batch_stats', mutates=('running_mean', 'running_var'))
 def bn_batch_stats(x: Tensor, running_mean: Optional[Tensor], running_var: Optional[Tensor], momentum: float,
                    eps: float) -> Tuple[Tensor, Tensor]:
     """(mean, invstd) over the rows of x; the running buffers are updated in place with torch's rule
@@ -530,7 +605,7 @@ def _(x, running_mean, running_var, momentum, eps):
     return x.new_empty(x.size(1)), x.new_empty(x.size(1))
 
 
-@torch.library.custom_op('gnnb200::bn_act', mutates_args=())
+@_op('bn_act')
 def bn_act(x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, relu: bool, drop_p: float,
            seed: int, training: bool, rows_total: int = 0) -> Tensor:
     """y = drop(relu((x - mean) * invstd * gamma + beta)).  training=True means mean/invstd are the batch
@@ -563,7 +638,7 @@ def _bn_bwd_call(phase: int, g: Tensor, x: Tensor, mean, invstd, gamma, beta, re
              _ptr(dgamma), _ptr(dbeta), stream=_stream(x))
 
 
-@torch.library.custom_op('gnnb200::bn_act_bwd', mutates_args=())
+@_op('bn_act_bwd')
 def bn_act_bwd(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor, relu: bool,
                drop_p: float, seed: int, training: bool) -> Tuple[Tensor, Tensor, Tensor]:
     """Single-device backward: (grad_x, dgamma, dbeta)."""
@@ -582,7 +657,7 @@ def _(grad_y, x, mean, invstd, gamma, beta, relu, drop_p, seed, training):
     return torch.empty_like(x), x.new_empty(x.size(1)), x.new_empty(x.size(1))
 
 
-@torch.library.custom_op('gnnb200::bn_act_bwd_reduce', mutates_args=())
+@_op('bn_act_bwd_reduce')
 def bn_act_bwd_reduce(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor,
                       relu: bool, drop_p: float, seed: int) -> Tensor:
     """Phase 1 of the partitioned backward: this shard's [2, C] = (dgamma, dbeta) partial sums."""
@@ -598,7 +673,7 @@ def _(grad_y, x, mean, invstd, gamma, beta, relu, drop_p, seed):
     return x.new_empty(2, x.size(1))
 
 
-@torch.library.custom_op('gnnb200::bn_act_bwd_apply', mutates_args=())
+@_op('bn_act_bwd_apply')
 def bn_act_bwd_apply(grad_y: Tensor, x: Tensor, mean: Tensor, invstd: Tensor, gamma: Tensor, beta: Tensor,
                      dgamma_dbeta: Tensor, relu: bool, drop_p: float, seed: int, rows_total: int) -> Tensor:
     """Phase 2: grad_x of this shard from the all-reduced (dgamma, dbeta) and the global row count."""
@@ -643,7 +718,7 @@ bn_act.register_autograd(_bn_backward, setup_context=_bn_setup)
 # ---------------------------------------------------------------------------------------------
 # link-prediction decoder features
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('gnnb200::lp_features', mutates_args=())
+@_op('lp_features')
 def lp_features(h: Tensor, edges: Tensor) -> Tensor:
     """[E, 3H] = [h_u + h_v, h_u * h_v, |h_u - h_v|] for edges int64 [2, E]."""
     _need_cuda(h, edges)
@@ -661,7 +736,7 @@ def _(h, edges):
     return h.new_empty(edges.size(1), 3 * h.size(1))
 
 
-@torch.library.custom_op('gnnb200::lp_features_bwd', mutates_args=())
+@_op('lp_features_bwd')
 def lp_features_bwd(grad_feat: Tensor, h: Tensor, edges: Tensor) -> Tensor:
     _need_cuda(grad_feat, h, edges)
     g, h = _rowmajor(grad_feat), _rowmajor(h)
@@ -697,7 +772,7 @@ lp_features.register_autograd(_lpf_backward, setup_context=_lpf_setup)
 # ---------------------------------------------------------------------------------------------
 # NT-Xent
 # ---------------------------------------------------------------------------------------------
-@torch.library.custom_op('gnnb200::ntxent_fwd', mutates_args=())
+@_op('ntxent_fwd')
 def ntxent_fwd(z: Tensor, temperature: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """(loss [1], zn [2M,D], lse [2M], norm [2M]) for z = cat(view1, view2) [2M, D]."""
     _need_cuda(z)
@@ -719,7 +794,7 @@ def _(z, temperature):
     return z.new_empty(1), torch.empty_like(z), z.new_empty(R), z.new_empty(R)
 
 
-@torch.library.custom_op('gnnb200::ntxent_bwd', mutates_args=())
+@_op('ntxent_bwd')
 def ntxent_bwd(grad_loss: Tensor, zn: Tensor, lse: Tensor, norm: Tensor, temperature: float) -> Tensor:
     _need_cuda(grad_loss, zn, lse, norm)
     R, D = zn.size(0), zn.size(1)
