@@ -163,7 +163,7 @@ def run_product(args):
     if world > 1:
         from gnnb200 import partition
         runner = partition.PartitionedBackboneStep(prod, dev, C5_F, HIDDEN, LAYERS, n, rank, world)
-        one_step = lambda x, ei: runner.step(x, ei)  # noqa: E731
+        one_step = lambda x, ei, local=False: runner.step(x, ei, local)  # noqa: E731
     else:
         model = build_model(prod, dev, C5_F)
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
@@ -200,8 +200,20 @@ def run_product(args):
     value = e * LAYERS * 2 / (ms_per_step / 1e3)
 
     # ---- end-to-end leg: host buffers, H2D of the step's inputs and D2H of the loss every step ----
-    x_host = x_dev.cpu().pin_memory()
-    ei_host = ei_dev.cpu().pin_memory()
+    # Multi-GPU: every rank reads only ITS share from the host — its row shard of x and a 1/N slice of the
+    # edge columns; the slices are all-gathered over NVLink inside the timed step to rebuild edge_index.
+    if world > 1:
+        from gnnb200.partition import shard_bounds
+        lo, hi, _ = shard_bounds(n, rank, world)
+        per_e = (e + world - 1) // world
+        e_lo, e_hi = min(e, rank * per_e), min(e, (rank + 1) * per_e)
+        x_host = x_dev[lo:hi].cpu().pin_memory()
+        ei_slice = torch.full((2, per_e), -1, dtype=torch.long)
+        ei_slice[:, : e_hi - e_lo] = ei_dev[:, e_lo:e_hi].cpu()
+        ei_host = ei_slice.pin_memory()
+    else:
+        x_host = x_dev.cpu().pin_memory()
+        ei_host = ei_dev.cpu().pin_memory()
     del x_dev, ei_dev, data
     torch.cuda.empty_cache()
 
@@ -225,7 +237,14 @@ def run_product(args):
         xd.record_stream(torch.cuda.current_stream(dev))
         eid.record_stream(torch.cuda.current_stream(dev))
         pending[0] = upload()                      # next step's H2D overlaps this step's compute
-        loss = one_step(xd, eid)
+        if world > 1:
+            parts = eid.new_empty(world, 2, eid.size(1))
+            dist.all_gather_into_tensor(parts.view(world * 2, -1), eid)
+            full = parts.permute(1, 0, 2).reshape(2, -1)
+            full = full[:, full[0] >= 0]           # drop the padding columns of the last slice
+            loss = one_step(xd, full, True)
+        else:
+            loss = one_step(xd, eid)
         return float(loss.detach().cpu())          # D2H read of the step's result
 
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,7 +274,9 @@ def run_product(args):
         n_local = (n + world - 1) // world
         e_local = e // world
         agg_bytes = aggregation_bytes(n_local, e_local, HIDDEN)
-        agg_avg = statistics.mean(agg_ms) if agg_ms else None
+        # one aggregation PASS = one launch on a single GPU, `chunks` launches (one per halo piece) when partitioned
+        passes = args.steps * LAYERS * 2
+        agg_avg = (sum(agg_ms) / passes) if agg_ms else None
         achieved = agg_bytes / (agg_avg / 1e3) / 1e9 if agg_avg else None
         traffic = None
         prof = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -280,7 +301,7 @@ def run_product(args):
             'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM,2,6> (fwd and transposed bwd)',
                          'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                          'frac': achieved / pk['hbm_gbs'] if achieved else None, 'traffic': traffic,
-                         'peak_source': pk['source'], 'launches_timed': len(agg_ms),
+                         'peak_source': pk['source'], 'launches_timed': len(agg_ms), 'passes_timed': passes,
                          'avg_launch_ms': agg_avg, 'algorithmic_bytes_per_launch': agg_bytes,
                          'share_of_step': (sum(agg_ms) / ms) if agg_ms else None},
         }

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libgnnb200.so')
 
 OK, EINVAL, ERANGE, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
 AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
+AGG_ACCUMULATE = 8
 POOL_SUM, POOL_MEAN, POOL_MAX = 0, 1, 2
 GEMM_F32, GEMM_TF32, GEMM_AUTO = 0, 1, 2
 EPI_NONE, EPI_RELU = 0, 1

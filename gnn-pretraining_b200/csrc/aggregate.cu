@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256, MINB)
 aggregate_vec_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ col, int64_t num_rows, int feat,
                      const float* __restrict__ self_x, int64_t lds, const float* __restrict__ eps_ptr,
-                     const float* __restrict__ dinv, float* __restrict__ out, int64_t ldo) {
+                     const float* __restrict__ dinv, float* __restrict__ out, int64_t ldo, int accumulate) {
   // U = neighbour rows in flight per group
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);                 // lane inside the row group
@@ -27,7 +27,12 @@ aggregate_vec_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __
 
   float4 acc[V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = 0; v < V; ++v) {
+    // accumulate: continue a sum started by an earlier pass over another column block of the same rows
+    // (chunked halo exchange, gnnb200/partition.py); the order of additions stays fixed
+    acc[v] = (accumulate && gl + v * G < nvec) ? *reinterpret_cast<const float4*>(out + row * ldo + 4 * (gl + v * G))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float di = 0.f;
   if (MODE == GNNB200_AGG_GCN) di = dinv[row];
 
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(256)
 aggregate_scalar_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
                         const int32_t* __restrict__ col, int64_t num_rows, int feat,
                         const float* __restrict__ self_x, int64_t lds, const float* __restrict__ eps_ptr,
-                        const float* __restrict__ dinv, float* __restrict__ out, int64_t ldo) {
+                        const float* __restrict__ dinv, float* __restrict__ out, int64_t ldo, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= num_rows) return;
@@ -100,7 +105,7 @@ aggregate_scalar_kernel(const float* __restrict__ x, int64_t ldx, const int32_t*
   if (self_x != nullptr) scale = (MODE == GNNB200_AGG_GCN) ? __fmul_rn(di, di) : __fadd_rn(1.0f, eps_ptr ? *eps_ptr : 0.f);
   const float cnt = (float)max(end - beg, 1);
   for (int f = lane; f < feat; f += 32) {
-    float acc = 0.f;
+    float acc = accumulate ? out[row * ldo + f] : 0.f;
     for (int e = beg; e < end; ++e) {
       const int c = col[e];
       const float v = __ldg(x + (int64_t)c * ldx + f);
@@ -113,7 +118,7 @@ aggregate_scalar_kernel(const float* __restrict__ x, int64_t ldx, const int32_t*
 }
 
 template <int G, int V>
-static int launch_vec(int mode, const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
+static int launch_vec(int mode, int accumulate, const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
                       int64_t num_rows, int feat, const float* self_x, int64_t lds, const float* eps,
                       const float* dinv, float* out, int64_t ldo, cudaStream_t stream) {
   const int block = 256;
@@ -126,13 +131,13 @@ static int launch_vec(int mode, const float* x, int64_t ldx, const int32_t* rowp
   constexpr int MINB = (V <= 2) ? 6 : ((V == 4) ? 3 : 2);
   switch (mode) {
     case GNNB200_AGG_SUM:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
+      aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
     case GNNB200_AGG_MEAN:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_MEAN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
+      aggregate_vec_kernel<G, V, GNNB200_AGG_MEAN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
     default:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_GCN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo);
+      aggregate_vec_kernel<G, V, GNNB200_AGG_GCN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
   }
   GNNB200_LAUNCH_CHECK();
@@ -148,7 +153,10 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
                                      const float* eps, const float* dinv, float* out, int64_t ldo,
                                      gnnb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int accumulate = (mode & GNNB200_AGG_ACCUMULATE) ? 1 : 0;
+  mode &= ~GNNB200_AGG_ACCUMULATE;
   if (num_rows < 0 || feat < 0 || mode < 0 || mode > 2) return GNNB200_EINVAL;
+  if (accumulate && mode != GNNB200_AGG_SUM) return GNNB200_EINVAL;
   if (num_rows == 0 || feat == 0) return GNNB200_OK;
   if (!x || !rowptr || !out) return GNNB200_EINVAL;
   if (mode == GNNB200_AGG_GCN && (!dinv || !self_x)) return GNNB200_EINVAL;
@@ -157,7 +165,7 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
                       ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)self_x % 16 == 0) &&
                       feat <= 1024;
   const int f = (int)feat;
-#define GNNB200_AGG_ARGS mode, x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, stream
+#define GNNB200_AGG_ARGS mode, accumulate, x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, stream
   if (vec_ok) {
     const int nvec = f / 4;
     if (nvec <= 4) return launch_vec<4, 1>(GNNB200_AGG_ARGS);
@@ -173,13 +181,13 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
   const unsigned grid = (unsigned)((num_rows * 32 + block - 1) / block);
   switch (mode) {
     case GNNB200_AGG_SUM:
-      aggregate_scalar_kernel<GNNB200_AGG_SUM><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo);
+      aggregate_scalar_kernel<GNNB200_AGG_SUM><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
     case GNNB200_AGG_MEAN:
-      aggregate_scalar_kernel<GNNB200_AGG_MEAN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo);
+      aggregate_scalar_kernel<GNNB200_AGG_MEAN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
     default:
-      aggregate_scalar_kernel<GNNB200_AGG_GCN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo);
+      aggregate_scalar_kernel<GNNB200_AGG_GCN><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
   }
   GNNB200_LAUNCH_CHECK();
@@ -197,7 +205,7 @@ extern "C" int gnnb200_dev_aggregate_variant(const float* x, const int32_t* rowp
   {                                                                                                                  \
     const unsigned grid = (unsigned)((num_rows * G + 255) / 256);                                                    \
     aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, 256, 0, stream>>>(x, ld, rowptr, col, num_rows, feat, \
-                                                                                   x, ld, eps, nullptr, out, ld);    \
+                                                                                   x, ld, eps, nullptr, out, ld, 0); \
   }
   switch (variant) {
     case 0: GNNB200_VARIANT(32, 2, 4, 1) break;

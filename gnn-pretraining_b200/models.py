@@ -52,7 +52,7 @@ class InputEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         # Linear -> [BatchNorm + ReLU + Dropout in one pass]; p follows self.dropout.p like the reference
-        return self.batch_norm(self.linear(x), drop_p=self.dropout.p)
+        return self.batch_norm(self.linear(x, bias_feeds_norm=True), drop_p=self.dropout.p)
 
 
 class GINLayer(nn.Module):
@@ -70,8 +70,8 @@ class GINLayer(nn.Module):
         # 5 kernels per layer forward: gather(+self term) -> GEMM -> BN+ReLU -> GEMM(+residual h) -> BN+ReLU+dropout
         mlp = self.gin_conv.nn
         z = self.gin_conv.aggregate(h, edge_index)
-        z = mlp[2](mlp[1](mlp[0](z)))
-        z = mlp[3](z, residual=h)
+        z = mlp[2](mlp[1](mlp[0](z, bias_feeds_norm=True)))
+        z = mlp[3](z, residual=h, bias_feeds_norm=True)
         return self.batch_norm(z, drop_p=DROPOUT_RATE)
 
 

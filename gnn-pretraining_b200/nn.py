@@ -36,11 +36,11 @@ class Linear(torch.nn.Linear):
 
     precision: Optional[str] = None
 
-    def forward(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+    def forward(self, x: Tensor, residual: Optional[Tensor] = None, bias_feeds_norm: bool = False) -> Tensor:
         prec = ops.PRECISIONS[self.precision or _default_precision]
         lead = x.shape[:-1]
         res = None if residual is None else residual.reshape(-1, self.out_features)
-        y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec, res)
+        y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec, res, bias_feeds_norm and self.training)
         return y.view(*lead, self.out_features)
 
 

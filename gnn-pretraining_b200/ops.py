@@ -241,11 +241,15 @@ def _(edge_index, num_nodes):
 # aggregation
 # ---------------------------------------------------------------------------------------------
 def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Optional[Tensor],
-                   eps: Optional[Tensor], dinv: Optional[Tensor]) -> Tensor:
+                   eps: Optional[Tensor], dinv: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
+    """out given => accumulate into it (GNNB200_AGG_ACCUMULATE): a later pass of a chunked aggregation."""
     _need_cuda(x, rowptr, col, self_x, eps, dinv)
     x = _rowmajor(x)
     n_rows = rowptr.numel() - 1
-    out = torch.empty(n_rows, x.size(1), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(n_rows, x.size(1), dtype=torch.float32, device=x.device)
+    else:
+        mode |= L.AGG_ACCUMULATE
     if self_x is not None:
         self_x = _rowmajor(self_x)
     timer = AGG_TIMER
@@ -540,19 +544,23 @@ def _(x):
 
 @_op('linear')
 def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int,
-           residual: Optional[Tensor] = None) -> Tensor:
+           residual: Optional[Tensor] = None, bias_feeds_norm: bool = False) -> Tensor:
     """y = x W^T + b (+ residual) with W [out, in] (nn.Linear layout); the residual add (GINLayer's
-    `gin_conv(h) + h`) happens in the GEMM epilogue."""
+    `gin_conv(h) + h`) happens in the GEMM epilogue.  bias_feeds_norm=True declares that y goes straight
+    into a training-mode BatchNorm: d(loss)/d(bias) is then identically zero (the batch mean absorbs any
+    constant shift), so the backward writes zeros instead of reducing grad_y over its rows (the reference
+    computes the same quantity numerically and gets rounding noise around 0)."""
     return _gemm_raw(x, False, weight, True, bias, False, precision, residual)
 
 
 @linear.register_fake
-def _(x, weight, bias, precision, residual=None):
+def _(x, weight, bias, precision, residual=None, bias_feeds_norm=False):
     return x.new_empty(x.size(0), weight.size(0))
 
 
 def _lin_setup(ctx, inputs, output):
-    x, weight, bias, precision, residual = inputs
+    x, weight, bias, precision, residual, bias_feeds_norm = inputs
+    ctx.zero_bias_grad = bias_feeds_norm
     ctx.precision = precision
     ctx.has_bias = bias is not None
     ctx.has_residual = residual is not None
@@ -568,9 +576,9 @@ def _lin_backward(ctx, g):
     if ctx.needs_input_grad[1]:
         gw = gemm(g, True, x, False, None, False, ctx.precision)            # [out,M] x [M,in]
     if ctx.has_bias and ctx.needs_input_grad[2]:
-        gb = colsum(g)
+        gb = torch.zeros(g.size(1), dtype=g.dtype, device=g.device) if ctx.zero_bias_grad else colsum(g)
     gres = g if (ctx.has_residual and ctx.needs_input_grad[4]) else None
-    return gx, gw, gb, None, gres
+    return gx, gw, gb, None, gres, None
 
 
 linear.register_autograd(_lin_backward, setup_context=_lin_setup)

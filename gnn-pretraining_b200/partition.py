@@ -3,7 +3,8 @@ SURVEY.md §5.8b / §8e — a capability the reference does not have: it is sing
 
 Rank r owns the contiguous destination-row range [lo_r, hi_r).  Per layer:
   forward : h_full = all_gather(h_local)                  (NCCL over NVLink; every row crosses once)
-            z_local = CSR_r gather over h_full + (1+eps) h_local      (rows of this rank only)
+            z_local = CSR_r gather over h_full + (1+eps) h_local      (rows of this rank only);
+            the exchange is cut into pieces and piece c+1 is in flight while piece c is being gathered
             dense transforms on local rows; BatchNorm statistics reduced over all ranks (Chan merge of the
             per-rank (n, sum, m2) in rank order -> every rank holds bit-identical statistics)
   backward: g_full = all_gather(g_local);  dh_local = CSC_r gather over g_full + (1+eps) g_local
@@ -32,24 +33,46 @@ def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
 
 
 class PartitionedGraph:
-    """This rank's slice of the graph: CSR over its destination rows (columns = global source ids) and
-    CSC over its source rows (columns = global destination ids).  Passed wherever the backbone expects
-    ``edge_index``; GINConv recognises it and takes the partitioned aggregation."""
+    """This rank's slice of the graph.  Passed wherever the backbone expects ``edge_index``; GINConv
+    recognises it and takes the partitioned aggregation.
 
-    def __init__(self, edge_index: Tensor, num_nodes: int, rank: int, world: int, group=None):
+    The halo exchange is pipelined: every rank's row shard is cut into ``chunks`` pieces; piece c of all
+    ranks is all-gathered (NCCL, asynchronously) while the gather over piece c-1 runs.  For that the
+    local CSR (rows = own destinations) and CSC (rows = own sources) are each built as ``chunks``
+    sub-structures in one stable sort with the composite key ``chunk * n_local + local_row``; their
+    column ids index the gathered piece buffer ``[world, rows_per_chunk, F]``.  A row's sum is continued
+    from pass to pass in a fixed order (piece 0 edges in edge order, then piece 1, ...), so results are
+    deterministic; they differ from the single-device edge order only by fp32 re-association."""
+
+    def __init__(self, edge_index: Tensor, num_nodes: int, rank: int, world: int, group=None, chunks: int = 4):
         self.num_nodes, self.rank, self.world, self.group = int(num_nodes), rank, world, group
         self.lo, self.hi, self.per = shard_bounds(self.num_nodes, rank, world)
         self.n_local = self.hi - self.lo
+        self.chunks = max(1, min(int(chunks), self.per)) if world > 1 else 1
+        self.rpc = (self.per + self.chunks - 1) // self.chunks            # rows per piece of one shard
+        n_rows = max(self.n_local, 1)
         src, dst = edge_index[0], edge_index[1]
-        own_dst = (dst >= self.lo) & (dst < self.hi)
-        fwd = torch.stack([src[own_dst], dst[own_dst] - self.lo], dim=0)
-        self.rowptr, self.col, _ = ops.csr_build(fwd, max(self.n_local, 1), False)      # key = local dst
-        own_src = (src >= self.lo) & (src < self.hi)
-        bwd = torch.stack([src[own_src] - self.lo, dst[own_src]], dim=0)
-        self.rowptr_t, self.col_t, _ = ops.csr_build(bwd, max(self.n_local, 1), True)   # key = local src
-        if self.n_local == 0:
-            self.rowptr, self.rowptr_t = self.rowptr[:1], self.rowptr_t[:1]
-        self.local_edges = int(fwd.size(1))
+        self.rowptr, self.col, self.local_edges = self._build(src, dst, n_rows)       # own destinations
+        self.rowptr_t, self.col_t, _ = self._build(dst, src, n_rows)                  # own sources (transposed)
+
+    def _build(self, other: Tensor, mine: Tensor, n_rows: int):
+        """Sub-CSRs over the edges whose `mine` endpoint this rank owns; columns = `other` endpoints."""
+        own = (mine >= self.lo) & (mine < self.hi)
+        o, m = other[own], mine[own] - self.lo
+        if self.world == 1:
+            rowptr, col, _ = ops.csr_build(torch.stack([o, m], dim=0), n_rows, False)
+            return rowptr, col, int(m.numel())
+        owner = torch.div(o, self.per, rounding_mode='floor')
+        off = o - owner * self.per
+        piece = torch.div(off, self.rpc, rounding_mode='floor')
+        col_in_piece = owner * self.rpc + (off - piece * self.rpc)                   # index into [world, rpc, F]
+        key = piece * n_rows + m
+        rowptr, col, _ = ops.csr_build(torch.stack([col_in_piece, key], dim=0), self.chunks * n_rows, False)
+        return rowptr, col, int(m.numel())
+
+    def sub_rowptr(self, rowptr: Tensor, piece: int) -> Tensor:
+        n_rows = max(self.n_local, 1)
+        return rowptr[piece * n_rows: (piece + 1) * n_rows + 1]
 
     def all_gather_rows(self, x_local: Tensor) -> Tensor:
         """[N, F] from every rank's [n_local, F] shard (equal-size padded shards on the wire)."""
@@ -65,23 +88,51 @@ class PartitionedGraph:
         dist.all_gather_into_tensor(full, send, group=self.group)
         return full[: self.num_nodes]
 
+    def gather_pieces_async(self, x_local: Tensor):
+        """Start one asynchronous all-gather per piece; returns [(work, buffer [world*rpc, F]), ...]."""
+        f = x_local.size(1)
+        padded = x_local
+        if x_local.size(0) != self.chunks * self.rpc:
+            padded = x_local.new_zeros(self.chunks * self.rpc, f)
+            padded[: x_local.size(0)] = x_local
+        out = []
+        for c in range(self.chunks):
+            buf = x_local.new_empty(self.world * self.rpc, f)
+            work = dist.all_gather_into_tensor(buf, padded[c * self.rpc: (c + 1) * self.rpc], group=self.group,
+                                               async_op=True)
+            out.append((work, buf))
+        return out
+
+    def aggregate(self, x_local: Tensor, eps: Tensor, transposed: bool) -> Tensor:
+        """sum over this rank's rows of the (transposed) graph + (1+eps) * x_local, pipelined with the
+        halo exchange."""
+        rowptr, col = (self.rowptr_t, self.col_t) if transposed else (self.rowptr, self.col)
+        if self.world == 1:
+            return ops._aggregate_raw(x_local, rowptr, col, L.AGG_SUM, x_local, eps, None)
+        pieces = self.gather_pieces_async(x_local)
+        out = None
+        for c, (work, buf) in enumerate(pieces):
+            work.wait()                                   # current stream waits for piece c only
+            last = c == self.chunks - 1
+            out = ops._aggregate_raw(buf, self.sub_rowptr(rowptr, c), col, L.AGG_SUM,
+                                     x_local if last else None, eps if last else None, None, out)
+        return out
+
 
 class _PartitionedGINAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h_local: Tensor, eps: Tensor, graph: PartitionedGraph) -> Tensor:
         h_local = h_local.contiguous()
-        h_full = graph.all_gather_rows(h_local)
         ctx.graph = graph
         ctx.save_for_backward(h_local, eps)
-        return ops._aggregate_raw(h_full, graph.rowptr, graph.col, L.AGG_SUM, h_local, eps, None)
+        return graph.aggregate(h_local, eps, transposed=False)
 
     @staticmethod
     def backward(ctx, g_local: Tensor):
         graph = ctx.graph
         h_local, eps = ctx.saved_tensors
         g_local = g_local.contiguous()
-        g_full = graph.all_gather_rows(g_local)
-        gh = ops._aggregate_raw(g_full, graph.rowptr_t, graph.col_t, L.AGG_SUM, g_local, eps, None)
+        gh = graph.aggregate(g_local, eps, transposed=True)
         geps = ops.dot(g_local, h_local) if ctx.needs_input_grad[1] else None      # per-rank partial sum
         return gh, geps, None
 
@@ -167,9 +218,10 @@ class PartitionedBackboneStep:
         self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr)
         self.num_nodes, self.rank, self.world, self.group = num_nodes, rank, world, group
 
-    def step(self, x: Tensor, edge_index: Tensor) -> Tensor:
+    def step(self, x: Tensor, edge_index: Tensor, x_is_local: bool = False) -> Tensor:
+        """x: the full [N, F] feature matrix, or (x_is_local) just this rank's row shard."""
         graph = PartitionedGraph(edge_index, self.num_nodes, self.rank, self.world, self.group)
-        x_local = x[graph.lo:graph.hi]
+        x_local = x if x_is_local else x[graph.lo:graph.hi]
         self.opt.zero_grad(set_to_none=True)
         with partition_scope(graph):
             h = self.model['gnn_backbone'](self.model['input_encoder'](x_local), graph)

@@ -75,6 +75,7 @@ int gnnb200_coalesce_i64(const int64_t* edge_index, int64_t num_edges, int64_t n
 #define GNNB200_AGG_SUM 0
 #define GNNB200_AGG_MEAN 1
 #define GNNB200_AGG_GCN 2
+#define GNNB200_AGG_ACCUMULATE 8 /* OR into SUM: start each row's sum from the value already in out (chunked halo passes) */
 int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
                           int64_t num_rows, int64_t feat, int mode, const float* self_x, int64_t lds,
                           const float* eps, const float* dinv, float* out, int64_t ldo,

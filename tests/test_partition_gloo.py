@@ -57,6 +57,8 @@ def _worker(rank, world, port, n, e, f, out_dir):
         shell = partition.PartitionedGraph.__new__(partition.PartitionedGraph)
         shell.num_nodes, shell.rank, shell.world, shell.group = n, rank, world, None
         shell.lo, shell.hi, shell.per, shell.n_local = lo, hi, per, hi - lo
+        shell.chunks = 3
+        shell.rpc = (per + shell.chunks - 1) // shell.chunks
         own_dst = (ei[1] >= lo) & (ei[1] < hi)
         rp, col = _csr(ei[1][own_dst] - lo, ei[0][own_dst], hi - lo)
         own_src = (ei[0] >= lo) & (ei[0] < hi)
@@ -69,6 +71,22 @@ def _worker(rank, world, port, n, e, f, out_dir):
         assert torch.equal(g_full, gout)
         gh_loc = _oracle_agg(g_full, rpt, colt, gout[lo:hi], eps)
         torch.testing.assert_close(gh_loc, xr.grad[lo:hi], rtol=1e-5, atol=1e-5)
+
+        # ---- pipelined exchange: piece buffers + composite-key sub-CSRs reproduce the same rows ----
+        pieces = shell.gather_pieces_async(x[lo:hi])
+        own = (ei[1] >= lo) & (ei[1] < hi)
+        o, m = ei[0][own], ei[1][own] - lo
+        owner = o // per
+        off = o - owner * per
+        piece = off // shell.rpc
+        col_in_piece = owner * shell.rpc + (off - piece * shell.rpc)
+        acc = torch.zeros(hi - lo, f)
+        for c, (work, buf) in enumerate(pieces):
+            work.wait()
+            sel = piece == c
+            acc.index_add_(0, m[sel], buf[col_in_piece[sel]])
+        acc = acc + (1 + eps) * x[lo:hi]
+        torch.testing.assert_close(acc, z.detach()[lo:hi], rtol=1e-5, atol=1e-5)
 
         # ---- BatchNorm moments: Chan merge over ranks == moments of the whole activation ----
         a = torch.randn(n, 8, generator=g) * 3 + 10
