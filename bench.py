@@ -285,7 +285,7 @@ def run_product(args):
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32' if gnn.default_precision() == 'f32' else 'f32+tf32',
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': {'f32': 'f32', 'tf32': 'f32+tf32', 'tf32x3': 'f32 (dense transforms: 3xTF32 on tcgen05, fp32-class)'}[gnn.default_precision()],
             'data': 'synthetic',
             'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F,
                        'hidden': HIDDEN, 'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
@@ -477,7 +477,7 @@ def main():
     ap.add_argument('--impl', default='gnnb200', choices=['gnnb200', 'reference'])
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C5 graph (debug only; 1.0 = BASELINE config)')
     ap.add_argument('--locality', type=float, default=0.0, help='fraction of intra-block edges (0 = uniform random)')
-    ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32'])
+    ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3'])
     ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')

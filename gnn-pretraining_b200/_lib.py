@@ -13,7 +13,7 @@ OK, EINVAL, ERANGE, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
 AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
 AGG_ACCUMULATE = 8
 POOL_SUM, POOL_MEAN, POOL_MAX = 0, 1, 2
-GEMM_F32, GEMM_TF32, GEMM_AUTO = 0, 1, 2
+GEMM_F32, GEMM_TF32, GEMM_AUTO, GEMM_TF32X3, GEMM_AUTO_X3 = 0, 1, 2, 3, 4
 EPI_NONE, EPI_RELU = 0, 1
 
 P = c_void_p

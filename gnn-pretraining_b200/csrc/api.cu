@@ -10,7 +10,7 @@ int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B,
                         int64_t ldr);
 int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
-              int epilogue, void* workspace, size_t* workspace_bytes, cudaStream_t stream);
+              int epilogue, int x3, void* workspace, size_t* workspace_bytes, cudaStream_t stream);
 }  // namespace gnnb200
 
 extern "C" int gnnb200_version(void) { return 100; }
@@ -38,15 +38,17 @@ extern "C" int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const f
   if (precision == GNNB200_GEMM_F32)
     return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
                               workspace, workspace_bytes, stream);
-  if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_AUTO) {
+  if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_AUTO || precision == GNNB200_GEMM_TF32X3 ||
+      precision == GNNB200_GEMM_AUTO_X3) {
+    const int x3 = (precision == GNNB200_GEMM_TF32X3 || precision == GNNB200_GEMM_AUTO_X3) ? 1 : 0;
     // the support predicate only reads sizes, leading dimensions and pointer alignment; during the
     // workspace query C may be NULL (NULL is 16-byte aligned), so both phases take the same branch
     if (!gnnb200::gemm_tf32_supported(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, residual, ldr)) {
-      if (precision == GNNB200_GEMM_TF32) return GNNB200_EUNSUPPORTED;
+      if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_TF32X3) return GNNB200_EUNSUPPORTED;
       return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
                                 workspace, workspace_bytes, stream);
     }
-    return gnnb200::gemm_tf32(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
+    return gnnb200::gemm_tf32(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue, x3,
                               workspace, workspace_bytes, stream);
   }
   return GNNB200_EINVAL;

@@ -31,11 +31,12 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BK = 32;           // fp32 elements per stage along K = one 128-byte swizzle span
 constexpr int UMMA_K = 8;        // kind::tf32
-constexpr int kStages = 3;        // 3 x 48 KB operand stages + 8 epilogue transpose tiles fit the 227 KB of one SM
+constexpr int kMaxStages = 4;
+constexpr int kSmemBudget = 232448 - 1024;   // 227 KB per CTA minus the 1024 B alignment slack
 constexpr int kThreads = 384;     // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr int kTmemCols = 512;
-constexpr int kEpiPitch = 36;      // floats per row of the epilogue transpose tile (16 B aligned, conflict-free)
+constexpr int kEpiTileFloats = 32 * 32;   // per-warp epilogue transpose tile, XOR-swizzled (no padding)
 constexpr uint32_t kSpinLimit = 1u << 27;   // bounded mbarrier spin: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,19 +139,39 @@ struct Params {
   int debug;          // dev only (env GNNB200_GEMM_DEBUG): 1 = skip epilogue global stores, 2 = skip the whole epilogue body
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// X3 = error-compensated "3xTF32": every operand word v is split in shared memory into hi = v with the 13 low
+// mantissa bits cleared (exactly representable in tf32) and lo = v - hi (exact in fp32), and each K-step issues
+// three MMAs  hi*hi + hi*lo + lo*hi  into the same fp32 accumulator: the dropped lo*lo term and the tf32
+// truncation of lo are ~2^-21 relative, i.e. fp32-class results from the tf32 tensor pipe.
+template <int BN, bool X3>
+struct TileCfg {
+  static constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
+  static constexpr uint32_t kBBytes = BN * BK * 4;
+  static constexpr uint32_t kHiBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStageBytes = kHiBytes * (X3 ? 2 : 1);
+  static constexpr int kEpiBytes = kEpiWarps * kEpiTileFloats * 4;
+  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes) / (int)kStageBytes;
+  static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kEpiBytes + 1024;
+  static_assert(kStages >= 2, "tile does not fit shared memory");
+};
+
+template <int BN, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-  constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
-  constexpr uint32_t kBBytes = BN * BK * 4;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  using Cfg = TileCfg<BN, X3>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr uint32_t kABytes = Cfg::kABytes;
+  constexpr uint32_t kBBytes = Cfg::kBBytes;
+  constexpr uint32_t kHiBytes = Cfg::kHiBytes;
+  constexpr uint32_t kStageBytes = Cfg::kStageBytes;
   constexpr uint32_t kSlabBytes = BK * 128;   // MN-major: one 32-wide slab = BK rows x 128 B
   constexpr uint32_t kIdesc = make_idesc(BN, A_MN, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
-  float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes);                       // kEpiWarps x 32 x kEpiPitch
-  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
+  float* epi_smem = reinterpret_cast<float*>(smem + kStages * kStageBytes);                       // kEpiWarps swizzled 32x32 tiles
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], split_bar[kMaxStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -166,6 +187,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 2);       // one arrival per splitter warp (X3 only)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -207,7 +229,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          mbar_expect_tx(&full_bar[stage], kHiBytes);
           const int k0 = kb * BK;
           if (A_MN) {
 #pragma unroll
@@ -239,7 +261,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
@@ -252,13 +274,53 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                      : make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t db = B_MN ? make_desc(sb + k * 1024, kSlabBytes, 512, kLayoutSw128Base32)
                                      : make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
-            umma_tf32(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (X3) {
+              // lo tiles live kHiBytes above their hi twins (same layout): descriptor start address += kHiBytes >> 4
+              const uint64_t lo_off = (uint64_t)(kHiBytes >> 4);
+              umma_tf32(d_tmem, da + lo_off, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);   // lo(A) * hi(B)
+              umma_tf32(d_tmem, da, db + lo_off, kIdesc, 1u);                               // hi(A) * lo(B)
+              umma_tf32(d_tmem, da, db, kIdesc, 1u);                                        // hi(A) * hi(B)
+            } else {
+              umma_tf32(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);              // frees the smem stage once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);                  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== operand splitter (X3 only): hi/lo decomposition in shared memory =====================
+    if (X3) {
+      const int tid64 = (warp - 2) * 32 + lane;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb0, kb1, split;
+        tile_coords(t, m0, n0, kb0, kb1, split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);                 // TMA bytes have landed (hi region holds raw fp32)
+          uint4* hi = reinterpret_cast<uint4*>(smem + stage * kStageBytes);
+          uint4* lo = reinterpret_cast<uint4*>(smem + stage * kStageBytes + kHiBytes);
+#pragma unroll 4
+          for (int i = tid64; i < (int)(kHiBytes / 16); i += 64) {
+            const uint4 v = hi[i];
+            uint4 h, l;
+            h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+            hi[i] = h;
+            lo[i] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -281,7 +343,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // transposes its 32x32 chunk through a private smem tile (pitch 36 floats: conflict-free 128-bit
       // stores by row and 128-bit loads by quarter-warp) and writes 4 full 128-byte row segments per
       // instruction; bias / residual / ReLU are applied on the coalesced side.
-      float* stage = epi_smem + (warp - 4) * (32 * kEpiPitch);
+      float* stage = epi_smem + (warp - 4) * kEpiTileFloats;
       const int r_in = lane >> 3;                      // row inside a group of 4
       const int c4 = (lane & 7) << 2;                  // column (floats) inside the 32-wide chunk
       const int c_begin = half * kChunksPerWarp, c_end = c_begin + kChunksPerWarp;
@@ -308,9 +370,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tmem_ld_wait();
+        // staging tile: element (row r, 16-byte slot s) at float offset r*32 + ((s ^ (r & 7)) << 2): both the row-wise
+        // 128-bit stores and the quarter-warp row reads below are bank-conflict free without padding
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage + lane * kEpiPitch + j) =
+          *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) =
               make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         if (c + 1 < c_end) {                           // next chunk's TMEM load overlaps this chunk's stores
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + (c + 1) * 32), v);
@@ -326,7 +390,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + r_in;
           const int row = m0 + q * 32 + r;
-          float4 o = *reinterpret_cast<const float4*>(stage + r * kEpiPitch + c4);
+          float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2));
           if (row < p.M && col < p.N) {                 // N % 4 == 0 is guaranteed by the host
             if (!has_k) o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.splits == 1) {
@@ -426,35 +490,35 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
   return GNNB200_OK;
 }
 
-static int pick_bn(long long N) {
-  if (N % 256 == 0) return 256;
+static int pick_bn(long long N, bool x3) {
+  if (!x3 && N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
   if (N % 64 == 0) return 64;
-  if (N >= 256) return 256;   // ragged last tile: TMA zero-fills, the store masks (N % 4 == 0 required)
+  if (!x3 && N >= 256) return 256;   // ragged last tile: TMA zero-fills, the store masks (N % 4 == 0 required)
   if (N >= 128) return 128;
   return 64;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool X3>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)kStages * (BM * BK * 4 + BN * BK * 4) + kEpiWarps * 32 * kEpiPitch * 4 + 1024;
+  constexpr size_t smem = TileCfg<BN, X3>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
-    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, kThreads, smem, stream>>>(ma, mb, p);
+  gemm_tf32_kernel<BN, A_MN, B_MN, X3><<<grid, kThreads, smem, stream>>>(ma, mb, p);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
 
-template <int BN>
+template <int BN, bool X3>
 static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid,
                      cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, p, grid, stream);
-  if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, p, grid, stream);
-  if (a_mn && !b_mn) return launch<BN, true, false>(ma, mb, p, grid, stream);
-  return launch<BN, true, true>(ma, mb, p, grid, stream);
+  if (!a_mn && !b_mn) return launch<BN, false, false, X3>(ma, mb, p, grid, stream);
+  if (!a_mn && b_mn) return launch<BN, false, true, X3>(ma, mb, p, grid, stream);
+  if (a_mn && !b_mn) return launch<BN, true, false, X3>(ma, mb, p, grid, stream);
+  return launch<BN, true, true, X3>(ma, mb, p, grid, stream);
 }
 
 }  // namespace tc
@@ -474,9 +538,9 @@ int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B,
 
 int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
-              int epilogue, void* workspace, size_t* workspace_bytes, cudaStream_t stream) {
+              int epilogue, int x3, void* workspace, size_t* workspace_bytes, cudaStream_t stream) {
   using namespace tc;
-  const int bn = pick_bn(N);
+  const int bn = pick_bn(N, x3 != 0);
   const int m_tiles = (int)((M + BM - 1) / BM);
   const int n_tiles = (int)((N + bn - 1) / bn);
   const int k_blocks = (int)((K + BK - 1) / BK);
@@ -525,9 +589,14 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   }
   const long long total = tiles * splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  if (bn == 256) rc = launch_bn<256>(a_mn, b_mn, ma, mb, p, grid, stream);
-  else if (bn == 128) rc = launch_bn<128>(a_mn, b_mn, ma, mb, p, grid, stream);
-  else rc = launch_bn<64>(a_mn, b_mn, ma, mb, p, grid, stream);
+  if (x3) {
+    if (bn == 128) rc = launch_bn<128, true>(a_mn, b_mn, ma, mb, p, grid, stream);
+    else rc = launch_bn<64, true>(a_mn, b_mn, ma, mb, p, grid, stream);
+  } else {
+    if (bn == 256) rc = launch_bn<256, false>(a_mn, b_mn, ma, mb, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, false>(a_mn, b_mn, ma, mb, p, grid, stream);
+    else rc = launch_bn<64, false>(a_mn, b_mn, ma, mb, p, grid, stream);
+  }
   if (rc) return rc;
   if (splits > 1) {
     const long long mn = (long long)M * N;

@@ -471,7 +471,8 @@ rows_scatter.register_autograd(_rs_backward, setup_context=_rs_setup)
 # ---------------------------------------------------------------------------------------------
 # 'tf32' = tensor cores wherever the layout rules hold, FFMA elsewhere (e.g. N == 1, ld % 4 != 0);
 # 'tf32_strict' raises instead of taking the FFMA kernel.
-PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_AUTO, 'tf32_strict': L.GEMM_TF32}
+PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_AUTO, 'tf32_strict': L.GEMM_TF32,
+              'tf32x3': L.GEMM_AUTO_X3, 'tf32x3_strict': L.GEMM_TF32X3}
 
 
 def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor], relu: bool,

@@ -128,12 +128,15 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
  *   (residual fuses GINLayer's `gin_conv(h) + h`, src/models/gnn.py:41; may be NULL)
  *   A is [M,K] (transa=0) or [K,M] (transa=1); B is [K,N] (transb=0) or [N,K] (transb=1).
  * precision: F32 = fp32 FFMA (1e-5 class); TF32 = tcgen05.mma kind::tf32 with TMA-fed
- * shared-memory tiles and TMEM fp32 accumulators (2e-2 class).  TF32 needs a TMA-legal
+ * shared-memory tiles and TMEM fp32 accumulators (2e-2 class); TF32X3 = the same pipeline with every operand
+ * split in shared memory into hi + lo tf32 parts and three MMAs per K-step (fp32 class).  TF32 needs a TMA-legal
  * layout (16-byte aligned bases, ld % 4 == 0); otherwise GNNB200_EUNSUPPORTED.
  * ------------------------------------------------------------------------------------------ */
 #define GNNB200_GEMM_F32 0
 #define GNNB200_GEMM_TF32 1
 #define GNNB200_GEMM_AUTO 2 /* TF32 tensor path when the layout allows it, else the fp32 FFMA kernel */
+#define GNNB200_GEMM_TF32X3 3 /* error-compensated 3xTF32 on the tensor pipe: fp32-class (1e-5) accuracy */
+#define GNNB200_GEMM_AUTO_X3 4 /* TF32X3 when the layout allows it, else the fp32 FFMA kernel */
 #define GNNB200_EPI_NONE 0
 #define GNNB200_EPI_RELU 1
 int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,

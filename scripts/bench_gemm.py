@@ -7,7 +7,7 @@ from gnnb200 import ops
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 N = int(2_449_029 * scale)
 dev = 'cuda'
-P = ops.PRECISIONS['tf32_strict']
+P = ops.PRECISIONS[os.environ.get('PREC', 'tf32_strict')]
 def run(name, a, ta, b, tb, bias=None, res=None, iters=5):
     for _ in range(2): ops._gemm_raw(a, ta, b, tb, bias, False, P, res)
     torch.cuda.synchronize()

@@ -173,3 +173,31 @@ def test_linear_residual_epilogue(prec):
     assert _rel(y, (ref(x) + h).detach()) < tol
     assert _rel(xg.grad, xr.grad) < tol
     assert torch.equal(hg.grad.cpu(), go)
+
+
+# ---- 3xTF32: error-compensated split on the tensor pipe, fp32-class accuracy ----------------------------------
+@pytest.mark.parametrize('m,n,k', [(128, 128, 32), (4100, 512, 256), (4100, 256, 512), (333, 256, 100), (1000, 64, 96),
+                                   (777, 100, 256), (20000, 256, 256), (1, 256, 256)])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tf32x3_is_fp32_class(m, n, k, ta, tb):
+    g = torch.Generator().manual_seed(m + 5 * n + 11 * k)
+    if (ta and m % 4) or (not ta and k % 4) or (tb and k % 4) or (not tb and n % 4):
+        pytest.skip('TMA needs 16-byte row pitches')
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    bias = torch.randn(n, generator=g)
+    want = (a.t() if ta else a).double() @ (b.t() if tb else b).double() + bias.double()
+    got = ops.gemm(a.to(DEV), ta, b.to(DEV), tb, bias.to(DEV), False, ops.PRECISIONS['tf32x3_strict'])
+    assert _rel(got, want) < TOL_F32
+
+
+def test_gemm_tf32x3_split_k_and_residual():
+    g = torch.Generator().manual_seed(8)
+    dy = torch.randn(50000, 512, generator=g)
+    x = torch.randn(50000, 256, generator=g)
+    got = ops.gemm(dy.to(DEV), True, x.to(DEV), False, None, False, ops.PRECISIONS['tf32x3_strict'])
+    assert _rel(got, dy.double().t() @ x.double()) < 3e-5          # K = 50,000 fp32 accumulations
+    w = torch.randn(256, 512, generator=g)
+    res = torch.randn(50000, 256, generator=g)
+    got = ops._gemm_raw(dy.to(DEV), False, w.to(DEV), True, None, True, ops.PRECISIONS['tf32x3_strict'], res.to(DEV))
+    assert _rel(got, torch.relu(dy.double() @ w.double().t() + res.double())) < TOL_F32
