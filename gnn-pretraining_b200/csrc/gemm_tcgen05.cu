@@ -34,7 +34,7 @@ constexpr int UMMA_K = 8;        // kind::tf32
 constexpr int kMaxStages = 4;
 constexpr int kSmemBudget = 232448 - 1024;   // 227 KB per CTA minus the 1024 B alignment slack
 constexpr int kThreads = 384;     // 4 control warps + 8 epilogue warps
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;       // plain tf32: warps 4..11 run the epilogue; 3xTF32: warps 4..7 do, warps 2,3,8..11 split operands
 constexpr int kTmemCols = 512;
 constexpr int kEpiTileFloats = 32 * 32;   // per-warp epilogue transpose tile, XOR-swizzled (no padding)
 constexpr uint32_t kSpinLimit = 1u << 27;   // bounded mbarrier spin: trap instead of hanging the GPU
@@ -165,6 +165,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr uint32_t kBBytes = Cfg::kBBytes;
   constexpr uint32_t kHiBytes = Cfg::kHiBytes;
   constexpr uint32_t kStageBytes = Cfg::kStageBytes;
+  constexpr int kEpi = X3 ? 4 : kEpiWarps;            // epilogue warps
+  constexpr int kSplit = 6;                           // splitter warps (X3 only)
   constexpr uint32_t kSlabBytes = BK * 128;   // MN-major: one 32-wide slab = BK rows x 128 B
   constexpr uint32_t kIdesc = make_idesc(BN, A_MN, B_MN);
 
@@ -187,11 +189,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&split_bar[s], 2);       // one arrival per splitter warp (X3 only)
+      mbar_init(&split_bar[s], kSplit);  // one arrival per splitter warp (X3 only)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiWarps);
+      mbar_init(&tmem_empty[s], kEpi);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -291,10 +293,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (X3 && (warp == 2 || warp == 3 || warp >= 8)) {
     // ===================== operand splitter (X3 only): hi/lo decomposition in shared memory =====================
-    if (X3) {
-      const int tid64 = (warp - 2) * 32 + lane;
+    {
+      const int tid_s = (warp < 4 ? warp - 2 : warp - 6) * 32 + lane;      // 0 .. kSplit*32-1
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -305,7 +307,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint4* hi = reinterpret_cast<uint4*>(smem + stage * kStageBytes);
           uint4* lo = reinterpret_cast<uint4*>(smem + stage * kStageBytes + kHiBytes);
 #pragma unroll 4
-          for (int i = tid64; i < (int)(kHiBytes / 16); i += 64) {
+          for (int i = tid_s; i < (int)(kHiBytes / 16); i += kSplit * 32) {
             const uint4 v = hi[i];
             uint4 h, l;
             h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
@@ -323,13 +325,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..11) =====================
+  } else if (warp >= 4 && warp < 4 + kEpi) {
+    // ===================== epilogue (warps 4..4+kEpi-1) =====================
     // A warp may only touch TMEM lanes 32*(warp%4)..+31; two warps share each lane quarter and split the
     // accumulator's columns, so every SM sub-partition has two epilogue warps to interleave.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    constexpr int kChunksPerWarp = BN / 64;
+    constexpr int kChunksPerWarp = (BN / 32) / (kEpi / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
