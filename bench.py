@@ -358,6 +358,27 @@ def small_graph_steps(impl, device, steps, warmup):
     sync = (lambda: torch.cuda.synchronize()) if device.type == 'cuda' else (lambda: None)
     lists = _graph_lists()
     out = {}
+    # ---- C1: Cora-shaped backbone forward+backward (BASELINE configs[0]: 2,708 nodes, 10,556 edges, 1,433 feats, L=3) ----
+    from gnnb200 import synthetic as _syn
+    cora = _syn.cora_like(42)
+    torch.manual_seed(0)
+    c1 = torch.nn.ModuleDict({'input_encoder': models.InputEncoder(1433, HIDDEN), 'gnn_backbone': models.GINBackbone(3, HIDDEN)}).to(device)
+    c1.train()
+    cx, cei = cora['x'].to(device), cora['edge_index'].to(device)
+
+    def c1_step():
+        c1.zero_grad(set_to_none=True)
+        c1['gnn_backbone'](c1['input_encoder'](cx), cei.view_as(cei)).sum().backward()
+    for _ in range(warmup):
+        c1_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c1_step()
+    sync()
+    dt = (time.perf_counter() - t0) / steps
+    out['c1_cora_backbone_fwd_bwd_ms'] = dt * 1e3
+    out['c1_edges_per_s'] = 10556 * 3 * 2 / dt
     # ---- C2: graph-classification fine-tune step ----
     torch.manual_seed(0)
     ft = models.FinetuneGNN(device, 'ENZYMES', 'full_finetune')
