@@ -307,7 +307,7 @@ def run_product(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(args, budget_steps=1)
-        if world == 1 and args.secondary:
+        if world == 1 and not args.no_secondary:
             sec = small_graph_steps('gnnb200', dev, steps=40, warmup=6)
             if not args.no_cpu_baseline:
                 torch.set_num_threads(os.cpu_count() or 1)
@@ -502,7 +502,7 @@ def main():
     ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
-    ap.add_argument('--secondary', action='store_true', help='also time the small-graph configs (C2 fine-tune step, C3 s4 step)')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the small-graph configs (C1 backbone, C2 fine-tune step, C3 s4 step)')
     ap.add_argument('--only-secondary', action='store_true', help='time only the small-graph configs and print them')
     args = ap.parse_args()
     if args.only_secondary:

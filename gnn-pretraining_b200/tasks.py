@@ -153,7 +153,7 @@ class NodeContrastiveTask(BasePretrainTask):
 
     @staticmethod
     def _common_rows(view, masks) -> Tensor:
-        starts = view.ptr.tolist()
+        starts = getattr(view, '_ptr_host', None) or view.ptr.tolist()
         rows = [torch.nonzero(m, as_tuple=False).view(-1) + starts[g] for g, m in enumerate(masks)]
         return torch.cat(rows) if rows else torch.empty(0, dtype=torch.long, device=view.x.device)
 
