@@ -343,18 +343,20 @@ def _make_batch(data_mod, graphs, device):
 
 def small_graph_steps(impl, device, steps, warmup):
     """(fine-tune steps/s on C2, s4 pre-training steps/s on C3) for `impl` in {'gnnb200', 'oracle'}.
-    The s4 step = the 5 task losses of scheme s4 (src/pretrain/pretrain.py:50) on three domains + one backward
-    sweep per task (what gradient surgery drives, src/pretrain/gradient_surgery.py:18-21) + AdamW; the
-    PCGrad projection itself is host-side code outside the hot path."""
+    The s4 step follows run_training (src/pretrain/pretrain.py:124-153): the 5 task losses of scheme s4 on three
+    domains, gradient surgery (one backward per task + the PCGrad projection), gradient clipping, AdamW, temperature
+    step; logging / loss balancer (host scalars that never reach the gradients when > 1 task is active) are left out."""
     import random
     if impl == 'gnnb200':
         from gnnb200 import data as data_mod, models, tasks as task_mod
+        from gnnb200.gradient_surgery import GradientSurgery
     else:
         from oracle import modules as models
         from oracle import install_pyg_shim
         install_pyg_shim()
         import torch_geometric.data as data_mod
         task_mod = models
+        GradientSurgery = models.GradientSurgery
     sync = (lambda: torch.cuda.synchronize()) if device.type == 'cuda' else (lambda: None)
     lists = _graph_lists()
     out = {}
@@ -412,17 +414,16 @@ def small_graph_steps(impl, device, steps, warmup):
     gen = torch.Generator().manual_seed(42)
     random.seed(42)
 
+    surgery = GradientSurgery(device)
+
     def s4_step():
+        losses = {name: task.compute_loss(batches, gen)[0] for name, task in tasks.items()}
         popt.zero_grad(set_to_none=True)
-        total = 0.0
-        for name, task in tasks.items():
-            loss, _ = task.compute_loss(batches, gen)
-            loss.backward()
-            total = total + loss.detach()
+        surgery.apply_gradient_surgery(pm, losses, list(losses))
         torch.nn.utils.clip_grad_norm_(pm.parameters(), max_norm=0.5)
         popt.step()
         temp.step()
-        return total
+        return losses
     s4_steps = max(2, steps // 4)
     for _ in range(max(1, warmup // 2)):
         s4_step()

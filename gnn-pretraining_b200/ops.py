@@ -71,7 +71,7 @@ KERNELS_PER_CALL = {
     'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_colstats_f32': 2,
     'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
-    'gnnb200_ntxent_bwd_f32': 1,
+    'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2,
 }
 _calls = {}
 AGG_TIMER = None      # bench.py sets this to a list to collect (start, stop) CUDA events per aggregation launch
@@ -851,3 +851,34 @@ def _ntx_backward(ctx, g_loss, g_zn, g_lse, g_norm):
 
 
 ntxent_fwd.register_autograd(_ntx_backward, setup_context=_ntx_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient surgery on a flat buffer
+# ---------------------------------------------------------------------------------------------
+@_op('pcgrad')
+def pcgrad(task_grads: Tensor, seg_offsets: Tensor, present: Tensor, order: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """(out [P], has_out uint8 [S], counters int32 [T, S, 2]); see gnnb200_pcgrad_f32.
+    task_grads [T, P] fp32, seg_offsets int64 [S+1], present uint8 [T, S], order int32 [T] (all CUDA)."""
+    _need_cuda(task_grads, seg_offsets, present, order)
+    tg = task_grads.contiguous()
+    T, Pn = tg.shape
+    S = seg_offsets.numel() - 1
+    dev = tg.device
+    rank_of = torch.empty_like(order)
+    rank_of[order.long()] = torch.arange(T, dtype=order.dtype, device=dev)
+    work = torch.empty_like(tg)
+    out = torch.zeros(Pn, dtype=torch.float32, device=dev)
+    has_out = torch.zeros(S, dtype=torch.uint8, device=dev)
+    counters = torch.zeros(T, S, 2, dtype=torch.int32, device=dev)
+    L.check(_invoke('gnnb200_pcgrad_f32', _ptr(tg), _ptr(work), T, Pn, _ptr(seg_offsets.contiguous()), S,
+                    _ptr(present.contiguous()), _ptr(order.contiguous()), _ptr(rank_of), _ptr(out), _ptr(has_out),
+                    _ptr(counters), _stream(tg)), 'pcgrad')
+    return out, has_out, counters
+
+
+@pcgrad.register_fake
+def _(task_grads, seg_offsets, present, order):
+    S = seg_offsets.numel() - 1
+    return (task_grads.new_empty(task_grads.size(1)), task_grads.new_empty(S, dtype=torch.uint8),
+            task_grads.new_empty(task_grads.size(0), S, 2, dtype=torch.int32))

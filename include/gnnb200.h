@@ -204,6 +204,21 @@ int gnnb200_ntxent_bwd_f32(const float* zn, const float* lse, const float* norm,
                            int64_t two_m, int64_t dim, float temperature, float* grad_z, int64_t ldgz,
                            gnnb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradient surgery on a flat buffer (src/pretrain/gradient_surgery.py:41-101).
+ * task_grads [T, P] holds each task's gradient of every parameter (zeros where absent); the P
+ * parameters are cut into S tensors by seg_offsets [S+1]; present [T, S] says which task produced a
+ * gradient for which tensor; order [T] is the shuffled task order and rank_of [T] its inverse.
+ * Per tensor, task i is projected against the ORIGINAL gradients of the tasks before it in `order`
+ * (skip when either norm is 0; project when the dot product is negative), then out [P] receives, for the
+ * tensors present in order[0], the mean over the tasks that have them (has_out [S] marks those).
+ * work [T, P] is scratch; counters [T, S, 2] = (conflicts, projections) per task and tensor.
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_pcgrad_f32(const float* task_grads, float* work, int64_t num_tasks, int64_t num_params,
+                       const int64_t* seg_offsets, int64_t num_segments, const uint8_t* present,
+                       const int32_t* order, const int32_t* rank_of, float* out, uint8_t* has_out,
+                       int32_t* counters, gnnb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

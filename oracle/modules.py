@@ -600,3 +600,51 @@ def instantiate_tasks(model, active_tasks, grl_scheduler, temperature_scheduler)
         'domain_adv': lambda: DomainAdversarialTask(model, grl_scheduler),
     }
     return {name: table[name]() for name in active_tasks if name in table}
+
+
+# ---- gradient surgery (src/pretrain/gradient_surgery.py) ---------------------------------------------
+class GradientSurgery:
+    """gradient_surgery.py:7-103 — the reference's PCGrad variant: one backward per task, per-parameter-tensor
+    projection against the ORIGINAL gradients of the tasks earlier in a random.shuffle order, mean written only for
+    the parameters of the first shuffled task."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+
+    def apply_gradient_surgery(self, model, task_losses, task_names):
+        import random
+        if len(task_losses) <= 1:
+            return {}
+        per_task = {}
+        for name, loss in task_losses.items():
+            model.zero_grad(set_to_none=True)
+            loss.backward(retain_graph=True)
+            per_task[name] = {k: p.grad.clone().to(self.device) for k, p in model.named_parameters() if p.grad is not None}
+        order = list(task_names)
+        random.shuffle(order)
+        modified = {}
+        conflicts = projections = 0
+        for i, ti in enumerate(order):
+            modified[ti] = per_task[ti].copy()
+            for tj in order[:i]:
+                for key in modified[ti].keys():
+                    if key not in per_task[tj]:
+                        continue
+                    gi, gj = modified[ti][key].flatten(), per_task[tj][key].flatten()
+                    if gi.norm() == 0 or gj.norm() == 0:
+                        continue
+                    projections += 1
+                    d = torch.dot(gi, gj)
+                    if d < 0:
+                        conflicts += 1
+                        modified[ti][key] = (gi - (d / (gj.norm() ** 2)) * gj).reshape(modified[ti][key].shape)
+        final = {}
+        for key in per_task[order[0]].keys():
+            stack = [modified[t][key] for t in order if key in modified[t]]
+            if stack:
+                final[key] = torch.stack(stack).mean(dim=0)
+        for key, p in model.named_parameters():
+            if key in final:
+                p.grad = final[key].to(p.device)
+        return {'gradient_surgery/total_conflicts': conflicts, 'gradient_surgery/total_projections': projections,
+                'gradient_surgery/conflict_ratio': conflicts / max(projections, 1)}

@@ -106,3 +106,28 @@ def test_augmentation_draw_order_matches(ref):
         assert torch.equal(x.x, y.x) and torch.equal(x.edge_index, y.edge_index) and torch.equal(x.batch, y.batch)
     for la, lb in zip(views[0][2:], views[1][2:]):
         assert all(torch.equal(p, q) for p, q in zip(la, lb))
+
+
+def test_gradient_surgery_matches_reference(ref):
+    """oracle.GradientSurgery == reference GradientSurgery (same random.seed -> same shuffle), bit for bit."""
+    torch.manual_seed(0)
+
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.ModuleDict({'shared': torch.nn.Linear(6, 5), 'a': torch.nn.Linear(5, 3), 'b': torch.nn.Linear(5, 2),
+                                    'c': torch.nn.Linear(5, 4)})
+    x = torch.randn(20, 6)
+    results = []
+    for impl in (ref.gradient_surgery.GradientSurgery, orc.GradientSurgery):
+        m = make()
+        h = torch.tanh(m['shared'](x))
+        losses = {'t1': m['a'](h).pow(2).mean(), 't2': -m['b'](h).sum(), 't3': (m['c'](h) - 1).abs().mean() - m['a'](h).mean()}
+        random.seed(3)
+        metrics = impl(torch.device('cpu')).apply_gradient_surgery(m, losses, list(losses))
+        results.append((metrics, {k: (None if p.grad is None else p.grad.clone()) for k, p in m.named_parameters()}))
+    assert results[0][0] == results[1][0]
+    for k in results[0][1]:
+        a, b = results[0][1][k], results[1][1][k]
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(a, b), k
