@@ -438,6 +438,90 @@ def small_graph_steps(impl, device, steps, warmup):
 
 
 # ------------------------------------------------------------------------------------------------
+# C4: data-parallel pre-training of scheme s5 (BASELINE configs[3]) — `--workload c4`
+# ------------------------------------------------------------------------------------------------
+S5_TASKS = S4_TASKS + ['domain_adv']
+TU_DOMAINS = ['MUTAG', 'PROTEINS', 'NCI1', 'ENZYMES']
+
+
+def run_c4(args):
+    """Every rank trains the s5 multi-task step on its own 128 graphs (32 per TU-shaped domain, seed 42 + rank):
+    losses -> gradient surgery over the five main tasks -> domain-adversarial backward through the GRL accumulates
+    on top (src/pretrain/pretrain.py:145-150) -> one flat NCCL all-reduce of the gradients (mean) -> clip -> AdamW.
+    BatchNorm statistics stay per replica (DDP semantics).  Weak scaling: value = global steps/s (same on every N),
+    graphs/s = 128 * N * steps/s."""
+    import random
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import gnnb200  # noqa: F401
+    from gnnb200 import data as data_mod, models, partition, synthetic, tasks as task_mod
+    from gnnb200.gradient_surgery import GradientSurgery
+    torch.manual_seed(0)
+    pm = models.PretrainableGNN(dev, TU_DOMAINS, S5_TASKS)
+    pm.train()
+    opt = torch.optim.AdamW(pm.parameters(), lr=1e-4)
+    temp, grl = task_mod.TemperatureScheduler(1000), task_mod.GRLScheduler(50, 20)
+    grl.current_step = 600                                        # past the 40 % ramp start: lambda > 0
+    tasks = task_mod.instantiate_tasks(pm, S5_TASKS, grl, temp)
+    batches = {d: _make_batch(data_mod, synthetic.tu_like_graphs(d, 32, seed=42 + rank * 7 + i), dev)
+               for i, d in enumerate(TU_DOMAINS)}
+    gen = torch.Generator().manual_seed(42 + rank)
+    random.seed(42 + rank)
+    surgery = GradientSurgery(dev)
+
+    def step():
+        losses = {name: task.compute_loss(batches, gen)[0] for name, task in tasks.items()}
+        main = {k: v for k, v in losses.items() if k != 'domain_adv'}
+        opt.zero_grad(set_to_none=True)
+        surgery.apply_gradient_surgery(pm, main, list(main))
+        losses['domain_adv'].backward()
+        if world > 1:
+            partition.allreduce_gradients(pm)
+            for p in pm.parameters():
+                if p.grad is not None:
+                    p.grad.div_(world)
+        torch.nn.utils.clip_grad_norm_(pm.parameters(), max_norm=0.5)
+        opt.step()
+        grl.step()
+        temp.step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        step()
+    e.record()
+    barrier()
+    t = torch.tensor([s.elapsed_time(e)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / args.steps
+    out = None
+    if rank == 0:
+        out = {'metric': 'pretrain_steps_per_sec', 'value': 1e3 / ms, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
+               'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32+tf32', 'data': 'synthetic',
+               'config': {'workload': 'c4_s5_data_parallel', 'graphs_per_rank': 128, 'global_batch': 128 * world,
+                          'domains': TU_DOMAINS, 'tasks': S5_TASKS, 'graphs_per_sec': 128 * world * 1e3 / ms}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # CPU legs (the oracle = the reference's modules restated over the pure-PyTorch PyG shim)
 # ------------------------------------------------------------------------------------------------
 def cpu_sample_sizes(args):
@@ -505,6 +589,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
     ap.add_argument('--no-secondary', action='store_true', help='skip the small-graph configs (C1 backbone, C2 fine-tune step, C3 s4 step)')
     ap.add_argument('--only-secondary', action='store_true', help='time only the small-graph configs and print them')
+    ap.add_argument('--workload', default='c5', choices=['c5', 'c4'], help='c5 = headline (default); c4 = data-parallel s5 pre-training step')
     args = ap.parse_args()
     if args.only_secondary:
         import gnnb200  # noqa: F401
@@ -514,6 +599,11 @@ def main():
             torch.set_num_threads(os.cpu_count() or 1)
             sec['cpu_oracle'] = small_graph_steps('oracle', torch.device('cpu'), steps=4, warmup=1)
         print(json.dumps(sec), flush=True)
+        return
+    if args.workload == 'c4':
+        out = run_c4(args)
+        if out is not None:
+            print(json.dumps(out), flush=True)
         return
     if args.impl == 'reference':
         out = run_reference(args)
