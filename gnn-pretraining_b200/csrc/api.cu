@@ -10,7 +10,8 @@ int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B,
                         int64_t ldr);
 int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
-              int epilogue, int x3, void* workspace, size_t* workspace_bytes, cudaStream_t stream);
+              int epilogue, int x3, float* col_sum, float* col_m2, void* workspace, size_t* workspace_bytes,
+              cudaStream_t stream);
 }  // namespace gnnb200
 
 extern "C" int gnnb200_version(void) { return 100; }
@@ -29,15 +30,37 @@ extern "C" const char* gnnb200_error_string(int code) {
 
 extern "C" int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
                                 float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
-                                const float* residual, int64_t ldr, int epilogue, int precision, void* workspace,
-                                size_t* workspace_bytes, gnnb200_stream_t stream_) {
+                                const float* residual, int64_t ldr, int epilogue, int precision, float* col_sum,
+                                float* col_m2, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (M < 0 || N < 0 || K < 0 || !workspace_bytes) return GNNB200_EINVAL;
   if (M >= (int64_t)INT32_MAX || N >= (int64_t)INT32_MAX) return GNNB200_ERANGE;
   if (workspace && M > 0 && N > 0 && (!C || (K > 0 && (!A || !B)))) return GNNB200_EINVAL;
-  if (precision == GNNB200_GEMM_F32)
-    return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
-                              workspace, workspace_bytes, stream);
+  const bool want_stats = col_sum != nullptr || col_m2 != nullptr;
+  // FFMA path: the column statistics are a second pass over C (gnnb200_colstats_f32) sharing the caller's workspace
+  auto simt_with_stats = [&]() -> int {
+    size_t gemm_bytes = 0, stat_bytes = 0;
+    int rc = gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue, nullptr,
+                                &gemm_bytes, stream);
+    if (rc) return rc;
+    if (want_stats) {
+      rc = gnnb200_colstats_f32(C, ldc, M, N, col_sum, col_m2, nullptr, &stat_bytes, stream_);
+      if (rc) return rc;
+    }
+    const size_t need = gemm_bytes > stat_bytes ? gemm_bytes : stat_bytes;
+    if (!workspace) {
+      *workspace_bytes = need;
+      return GNNB200_OK;
+    }
+    if (*workspace_bytes < need) return GNNB200_EWORKSPACE;
+    size_t b = *workspace_bytes;
+    rc = gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue, workspace, &b,
+                            stream);
+    if (rc || !want_stats) return rc;
+    b = *workspace_bytes;
+    return gnnb200_colstats_f32(C, ldc, M, N, col_sum, col_m2, workspace, &b, stream_);
+  };
+  if (precision == GNNB200_GEMM_F32) return simt_with_stats();
   if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_AUTO || precision == GNNB200_GEMM_TF32X3 ||
       precision == GNNB200_GEMM_AUTO_X3) {
     const int x3 = (precision == GNNB200_GEMM_TF32X3 || precision == GNNB200_GEMM_AUTO_X3) ? 1 : 0;
@@ -45,11 +68,10 @@ extern "C" int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const f
     // workspace query C may be NULL (NULL is 16-byte aligned), so both phases take the same branch
     if (!gnnb200::gemm_tf32_supported(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, residual, ldr)) {
       if (precision == GNNB200_GEMM_TF32 || precision == GNNB200_GEMM_TF32X3) return GNNB200_EUNSUPPORTED;
-      return gnnb200::gemm_simt(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue,
-                                workspace, workspace_bytes, stream);
+      return simt_with_stats();
     }
     return gnnb200::gemm_tf32(A, lda, transa, B, ldb, transb, C, ldc, M, N, K, bias, residual, ldr, epilogue, x3,
-                              workspace, workspace_bytes, stream);
+                              col_sum, col_m2, workspace, workspace_bytes, stream);
   }
   return GNNB200_EINVAL;
 }

@@ -26,6 +26,8 @@
 
 namespace gnnb200 {
 
+int colstats_finish(const float* part, long long chunks, long long cols, float* sum, float* m2, cudaStream_t stream);
+
 namespace tc {
 
 constexpr int BM = 128;          // UMMA M (cta_group::1)
@@ -136,6 +138,7 @@ struct Params {
   const float* residual;  // [M,N] added in the epilogue (GINLayer's `+ h`), only when splits == 1
   long long ldr;
   int relu;
+  float* col_part;    // optional [m_tiles*4][3][N] per-32-row (count, sum, centred m2) of the written C columns (BN statistics)
   int debug;          // dev only (env GNNB200_GEMM_DEBUG): 1 = skip epilogue global stores, 2 = skip the whole epilogue body
 };
 
@@ -403,6 +406,51 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             }
             if (p.debug != 1) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+          } else {
+            o = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (p.col_part) *reinterpret_cast<float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2)) = o;   // final values, own slot
+        }
+        if (p.col_part) {
+          // BatchNorm statistics of the columns just written (saves the separate read pass over C): per 32-row block the
+          // sum and the second moment about the block's own mean, merged later with Chan's formula (fixed order).
+          const int row0 = m0 + q * 32;
+          const int n_valid = max(0, min(32, p.M - row0));
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_in;
+            const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2));
+            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+          }
+#pragma unroll
+          for (int sh = 8; sh <= 16; sh <<= 1) {
+            s4.x += __shfl_xor_sync(0xffffffffu, s4.x, sh); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, sh);
+            s4.z += __shfl_xor_sync(0xffffffffu, s4.z, sh); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, sh);
+          }
+          const float inv_n = n_valid > 0 ? 1.f / (float)n_valid : 0.f;
+          const float4 mu = make_float4(s4.x * inv_n, s4.y * inv_n, s4.z * inv_n, s4.w * inv_n);
+          float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_in;
+            if (row0 + r < p.M) {
+              const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((((lane & 7)) ^ (r & 7)) << 2));
+              const float dx = o.x - mu.x, dy = o.y - mu.y, dz = o.z - mu.z, dw = o.w - mu.w;
+              q4.x = fmaf(dx, dx, q4.x); q4.y = fmaf(dy, dy, q4.y); q4.z = fmaf(dz, dz, q4.z); q4.w = fmaf(dw, dw, q4.w);
+            }
+          }
+#pragma unroll
+          for (int sh = 8; sh <= 16; sh <<= 1) {
+            q4.x += __shfl_xor_sync(0xffffffffu, q4.x, sh); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, sh);
+            q4.z += __shfl_xor_sync(0xffffffffu, q4.z, sh); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, sh);
+          }
+          if (r_in == 0 && col < p.N && row0 < p.M) {
+            float* part = p.col_part + (long long)(row0 >> 5) * 3 * p.N;
+            const float nv = (float)n_valid;
+            *reinterpret_cast<float4*>(part + col) = make_float4(nv, nv, nv, nv);
+            *reinterpret_cast<float4*>(part + p.N + col) = s4;
+            *reinterpret_cast<float4*>(part + 2 * p.N + col) = q4;
           }
         }
         __syncwarp();                                   // the staging tile is reused by the next chunk
@@ -540,7 +588,8 @@ int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B,
 
 int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
-              int epilogue, int x3, void* workspace, size_t* workspace_bytes, cudaStream_t stream) {
+              int epilogue, int x3, float* col_sum, float* col_m2, void* workspace, size_t* workspace_bytes,
+              cudaStream_t stream) {
   using namespace tc;
   const int bn = pick_bn(N, x3 != 0);
   const int m_tiles = (int)((M + BM - 1) / BM);
@@ -555,10 +604,15 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
     if (splits > max_s) splits = max_s;
     if (splits < 1) splits = 1;
   }
+  const bool want_stats = col_sum != nullptr || col_m2 != nullptr;
+  if (want_stats && (M + 31) / 32 > 2147483647LL / 4) return GNNB200_ERANGE;
+  if (want_stats) splits = 1;      // statistics come from the fused epilogue
   const int kbps = (k_blocks + splits - 1) / splits;
   splits = (k_blocks + kbps - 1) / kbps;
+  const long long stat_blocks = (M + 31) / 32;
   Workspace ws(workspace);
   float* partial = splits > 1 ? ws.take<float>((size_t)splits * M * N) : nullptr;
+  float* col_part = want_stats ? ws.take<float>((size_t)stat_blocks * 3 * N) : nullptr;
   if (!workspace) {
     *workspace_bytes = ws.bytes();
     return GNNB200_OK;
@@ -585,6 +639,7 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   p.residual = splits > 1 ? nullptr : residual;
   p.ldr = ldr;
   p.relu = (splits == 1 && (epilogue & GNNB200_EPI_RELU)) ? 1 : 0;
+  p.col_part = col_part;
   {
     const char* dbg = getenv("GNNB200_GEMM_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
@@ -606,6 +661,7 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
                                                                                (epilogue & GNNB200_EPI_RELU) ? 1 : 0, C, ldc);
     GNNB200_LAUNCH_CHECK();
   }
+  if (want_stats) return colstats_finish(col_part, stat_blocks, N, col_sum, col_m2, stream);
   return GNNB200_OK;
 }
 

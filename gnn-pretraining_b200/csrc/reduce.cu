@@ -142,6 +142,14 @@ colstats_finish_kernel(const float* __restrict__ part, int chunks, int cols, flo
   }
 }
 
+// Shared with the GEMM epilogue's fused statistics: fold [chunks][3][cols] partials (count, sum, centred m2).
+int colstats_finish(const float* part, long long chunks, long long cols, float* sum, float* m2, cudaStream_t stream) {
+  if (cols <= 0) return GNNB200_OK;
+  colstats_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)chunks, (int)cols, sum, m2);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
 }  // namespace gnnb200
 
 using namespace gnnb200;

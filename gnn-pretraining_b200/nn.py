@@ -36,10 +36,17 @@ class Linear(torch.nn.Linear):
 
     precision: Optional[str] = None
 
-    def forward(self, x: Tensor, residual: Optional[Tensor] = None, bias_feeds_norm: bool = False) -> Tensor:
+    def forward(self, x: Tensor, residual: Optional[Tensor] = None, bias_feeds_norm: bool = False,
+                return_stats: bool = False):
+        """return_stats=True (2-D input): also returns (column sums, centred second moments) of the output, computed in
+        the GEMM epilogue, for the BatchNormAct that follows (pass them as ``stats=``)."""
         prec = ops.PRECISIONS[self.precision or _default_precision]
         lead = x.shape[:-1]
         res = None if residual is None else residual.reshape(-1, self.out_features)
+        if return_stats:
+            y, s, m2 = ops.linear_stats(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec, res,
+                                        bias_feeds_norm and self.training)
+            return y.view(*lead, self.out_features), (s.detach(), m2.detach())
         y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec, res, bias_feeds_norm and self.training)
         return y.view(*lead, self.out_features)
 
@@ -60,7 +67,8 @@ class BatchNormAct(torch.nn.BatchNorm1d):
         super().__init__(num_features, **kwargs)
         self.fused_relu = relu
 
-    def forward(self, x: Tensor, drop_p: float = 0.0) -> Tensor:
+    def forward(self, x: Tensor, drop_p: float = 0.0, stats=None) -> Tensor:
+        """stats = (column sums, centred second moments) of x when a producer already computed them."""
         use_batch_stats = self.training or self.running_mean is None
         p = float(drop_p) if self.training else 0.0
         fusable = (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and x.size(1) % 4 == 0
@@ -78,10 +86,16 @@ class BatchNormAct(torch.nn.BatchNorm1d):
             seed ^= (_partition.rank * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)      # independent masks per shard
             mean, invstd = part.synced_batch_stats(x, _partition.num_nodes, ops.SYNC_GROUP,
                                                    self.running_mean if upd else None, self.running_var if upd else None,
-                                                   float(self.momentum if self.momentum is not None else 0.0), float(self.eps))
+                                                   float(self.momentum if self.momentum is not None else 0.0), float(self.eps),
+                                                   stats)
             return ops.bn_act(x, mean, invstd, self.weight, self.bias, self.fused_relu, p, seed, True,
                               _partition.num_nodes)
-        if use_batch_stats:
+        if use_batch_stats and stats is not None:
+            upd = self.training and self.track_running_stats
+            mean, invstd = ops.bn_stats_finalize(stats[0], stats[1], x.size(0), self.running_mean if upd else None,
+                                                 self.running_var if upd else None,
+                                                 float(self.momentum if self.momentum is not None else 0.0), float(self.eps))
+        elif use_batch_stats:
             upd = self.training and self.track_running_stats
             mean, invstd = ops.bn_batch_stats(x.detach(), self.running_mean if upd else None,
                                               self.running_var if upd else None,

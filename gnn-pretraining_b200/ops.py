@@ -492,7 +492,8 @@ PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_AUTO, 'tf32_strict': L.GEMM_TF32
 
 
 def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor], relu: bool,
-              precision: int, residual: Optional[Tensor] = None) -> Tensor:
+              precision: int, residual: Optional[Tensor] = None, want_stats: bool = False):
+    """C = op(a) op(b) (+bias)(+residual)(ReLU); with want_stats also (column sums, centred second moments) of C."""
     _need_cuda(a, b, bias, residual)
     a, b = _rowmajor(a), _rowmajor(b)
     M, K = (a.size(1), a.size(0)) if transa else (a.size(0), a.size(1))
@@ -506,12 +507,16 @@ def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[T
         residual = _rowmajor(residual)
         if residual.shape != c.shape:
             raise L.Gnnb200Error(f'residual shape {tuple(residual.shape)} != output shape {tuple(c.shape)}')
+    csum = cm2 = None
+    if want_stats:
+        csum = torch.empty(N, dtype=torch.float32, device=a.device)
+        cm2 = torch.empty(N, dtype=torch.float32, device=a.device)
     _call_ws('gnnb200_gemm_f32', 'gemm', a.device, _ptr(a), _ld(a), int(transa), _ptr(b), _ld(b), int(transb),
              _ptr(c), _ld(c), M, N, K, _ptr(bias), _ptr(residual), _ld(residual) if residual is not None else 0,
-             L.EPI_RELU if relu else L.EPI_NONE, precision, stream=_stream(a),
+             L.EPI_RELU if relu else L.EPI_NONE, precision, _ptr(csum), _ptr(cm2), stream=_stream(a),
              key=(M, N, K, transa, transb, precision, _ld(a) % 4, _ld(b) % 4, residual is None or _ld(residual) % 4 == 0,
-                  a.data_ptr() % 16, b.data_ptr() % 16))
-    return c
+                  a.data_ptr() % 16, b.data_ptr() % 16, want_stats))
+    return (c, csum, cm2) if want_stats else c
 
 
 @_op('gemm')
@@ -603,6 +608,27 @@ def _lin_backward(ctx, g):
 linear.register_autograd(_lin_backward, setup_context=_lin_setup)
 
 
+@_op('linear_stats')
+def linear_stats(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int, residual: Optional[Tensor] = None,
+                 bias_feeds_norm: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """(y, colsum(y), centred second moment of y's columns): `linear` whose GEMM epilogue also produces the batch
+    statistics of the BatchNorm that consumes y (no separate read pass over y)."""
+    return _gemm_raw(x, False, weight, True, bias, False, precision, residual, True)
+
+
+@linear_stats.register_fake
+def _(x, weight, bias, precision, residual=None, bias_feeds_norm=False):
+    n = weight.size(0)
+    return x.new_empty(x.size(0), n), x.new_empty(n), x.new_empty(n)
+
+
+def _lin_stats_backward(ctx, g, g_sum, g_m2):
+    return _lin_backward(ctx, g)              # the statistics are consumed under no_grad (see bn_act's backward)
+
+
+linear_stats.register_autograd(_lin_stats_backward, setup_context=_lin_setup)
+
+
 # ---------------------------------------------------------------------------------------------
 # fused BatchNorm1d (+ReLU)(+dropout)
 # ---------------------------------------------------------------------------------------------
@@ -631,6 +657,25 @@ def bn_batch_stats(x: Tensor, running_mean: Optional[Tensor], running_var: Optio
 @bn_batch_stats.register_fake
 def _(x, running_mean, running_var, momentum, eps):
     return x.new_empty(x.size(1)), x.new_empty(x.size(1))
+
+
+@_op('bn_stats_finalize', mutates=('running_mean', 'running_var'))
+def bn_stats_finalize(col_sum: Tensor, col_m2: Tensor, rows: int, running_mean: Optional[Tensor],
+                      running_var: Optional[Tensor], momentum: float, eps: float) -> Tuple[Tensor, Tensor]:
+    """(mean, invstd) from column sums / centred second moments produced elsewhere (the GEMM epilogue); running
+    buffers updated in place like bn_batch_stats."""
+    _need_cuda(col_sum, col_m2, running_mean, running_var)
+    cols = col_sum.numel()
+    mean = torch.empty(cols, dtype=torch.float32, device=col_sum.device)
+    invstd = torch.empty(cols, dtype=torch.float32, device=col_sum.device)
+    L.check(_invoke('gnnb200_bn_finalize_f32', _ptr(col_sum), _ptr(col_m2), rows, cols, eps, momentum, _ptr(running_mean),
+                    _ptr(running_var), _ptr(mean), _ptr(invstd), _stream(col_sum)), 'bn_finalize')
+    return mean, invstd
+
+
+@bn_stats_finalize.register_fake
+def _(col_sum, col_m2, rows, running_mean, running_var, momentum, eps):
+    return torch.empty_like(col_sum), torch.empty_like(col_sum)
 
 
 @_op('bn_act')

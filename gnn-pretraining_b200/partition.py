@@ -173,10 +173,11 @@ def gather_moments(n_rows: int, s: Tensor, m2: Tensor, group) -> Tensor:
 
 
 def synced_batch_stats(x_local: Tensor, graph_rows_total: int, group, running_mean: Optional[Tensor],
-                       running_var: Optional[Tensor], momentum: float, eps: float) -> Tuple[Tensor, Tensor]:
+                       running_var: Optional[Tensor], momentum: float, eps: float, local_stats=None
+                       ) -> Tuple[Tensor, Tensor]:
     """Global (mean, invstd) of a row-partitioned activation: per-rank (n, sum, m2) gathered and merged with
     Chan's formula in rank order; running buffers updated from the global moments (torch's rule)."""
-    s, m2 = ops.colstats(x_local.detach())
+    s, m2 = local_stats if local_stats is not None else ops.colstats(x_local.detach())
     _, gsum, m2_tot = merge_moments(gather_moments(x_local.size(0), s, m2, group))
     mean_out = torch.empty_like(s)
     invstd = torch.empty_like(s)

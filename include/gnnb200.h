@@ -126,6 +126,9 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
  * Dense transforms (K3: nn.Linear of src/models/gnn.py:13,31,34 and src/models/heads.py:41).
  *   C[M,N] = op(A) * op(B) (+ bias[N]) (+ residual[M,N]) (ReLU)        op = identity or transpose
  *   (residual fuses GINLayer's `gin_conv(h) + h`, src/models/gnn.py:41; may be NULL)
+ *   col_sum / col_m2 (may be NULL): per-column sum and centred second moment of the written C, i.e. the
+ *   batch statistics of the BatchNorm that follows (src/models/gnn.py:15,32,38), computed in the epilogue
+ *   on the tensor path (no extra pass over C) and by a second pass on the FFMA path; not with ReLU.
  *   A is [M,K] (transa=0) or [K,M] (transa=1); B is [K,N] (transb=0) or [N,K] (transb=1).
  * precision: F32 = fp32 FFMA (1e-5 class); TF32 = tcgen05.mma kind::tf32 with TMA-fed
  * shared-memory tiles and TMEM fp32 accumulators (2e-2 class); TF32X3 = the same pipeline with every operand
@@ -141,8 +144,8 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
 #define GNNB200_EPI_RELU 1
 int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
                      float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
-                     const float* residual, int64_t ldr, int epilogue, int precision, void* workspace,
-                     size_t* workspace_bytes, gnnb200_stream_t stream);
+                     const float* residual, int64_t ldr, int epilogue, int precision, float* col_sum,
+                     float* col_m2, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
 
 /* Column statistics over rows (K4 BatchNorm1d batch stats of src/models/gnn.py:15,32,38 and bias
  * gradients): sum[c] = sum_r x[r,c]; when sumsq != NULL also the centred second moment

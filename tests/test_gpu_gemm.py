@@ -201,3 +201,21 @@ def test_gemm_tf32x3_split_k_and_residual():
     res = torch.randn(50000, 256, generator=g)
     got = ops._gemm_raw(dy.to(DEV), False, w.to(DEV), True, None, True, ops.PRECISIONS['tf32x3_strict'], res.to(DEV))
     assert _rel(got, torch.relu(dy.double() @ w.double().t() + res.double())) < TOL_F32
+
+
+@pytest.mark.parametrize('prec', ['tf32_strict', 'tf32x3_strict', 'f32'])
+@pytest.mark.parametrize('m,n,k', [(4100, 512, 256), (70001, 256, 512), (333, 256, 100), (31, 64, 64)])
+def test_gemm_epilogue_column_statistics(prec, m, n, k):
+    """BatchNorm batch statistics of the GEMM output come out of the epilogue (tensor path) / a second pass (FFMA):
+    they must equal the statistics of the C that was actually written."""
+    g = torch.Generator().manual_seed(m + n)
+    a = torch.randn(m, k, generator=g) + 0.5
+    w = torch.randn(n, k, generator=g)
+    bias = torch.randn(n, generator=g) * 3
+    res = torch.randn(m, n, generator=g)
+    c, s, m2 = ops._gemm_raw(a.to(DEV), False, w.to(DEV), True, bias.to(DEV), False, ops.PRECISIONS[prec], res.to(DEV), True)
+    cd = c.double().cpu()
+    assert _rel(s, cd.sum(0)) < 1e-5
+    assert _rel(m2, ((cd - cd.mean(0)) ** 2).sum(0)) < 1e-4
+    tol = TOL_F32 if prec != 'tf32_strict' else 5e-3
+    assert _rel(c, a.double() @ w.double().t() + bias.double() + res.double()) < tol
