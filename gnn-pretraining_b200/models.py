@@ -52,9 +52,6 @@ class InputEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         # Linear -> [BatchNorm + ReLU + Dropout in one pass]; p follows self.dropout.p like the reference
-        if self.training and x.dim() == 2:
-            y, stats = self.linear(x, bias_feeds_norm=True, return_stats=True)       # BN statistics from the GEMM epilogue
-            return self.batch_norm(y, drop_p=self.dropout.p, stats=stats)
         return self.batch_norm(self.linear(x, bias_feeds_norm=True), drop_p=self.dropout.p)
 
 
@@ -73,10 +70,9 @@ class GINLayer(nn.Module):
         # 5 kernels per layer forward: gather(+self term) -> GEMM -> BN+ReLU -> GEMM(+residual h) -> BN+ReLU+dropout
         mlp = self.gin_conv.nn
         z = self.gin_conv.aggregate(h, edge_index)
-        if self.training:
-            a1, st1 = mlp[0](z, bias_feeds_norm=True, return_stats=True)          # BN statistics from the GEMM epilogues
-            s, st2 = mlp[3](mlp[2](mlp[1](a1, stats=st1)), residual=h, bias_feeds_norm=True, return_stats=True)
-            return self.batch_norm(s, drop_p=DROPOUT_RATE, stats=st2)
+        # (Linear(..., return_stats=True) can hand the BatchNorm statistics over from the GEMM epilogue; measured on
+        # C5 it is slower — 265 vs 247 ms/step — because the K=256 GEMMs are epilogue-bound and 76k per-32-row partials
+        # per column have to be merged, so the separate column-statistics pass stays.)
         z = mlp[2](mlp[1](mlp[0](z, bias_feeds_norm=True)))
         z = mlp[3](z, residual=h, bias_feeds_norm=True)
         return self.batch_norm(z, drop_p=DROPOUT_RATE)
