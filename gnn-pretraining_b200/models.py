@@ -14,6 +14,9 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import ops
+from . import nn as _gnn
+from .fused import GINLayerFn
+from .graph import graph_of
 from .nn import BatchNormAct, FusedAwayReLU, GINConv, Linear, global_mean_pool
 
 # constants of the reference (src/models/gnn.py:6-8, heads.py:10-13, pretrain_model.py:18-20,
@@ -66,9 +69,20 @@ class GINLayer(nn.Module):
             train_eps=True)
         self.batch_norm = BatchNormAct(hidden_dim, relu=True)
 
+    fused = True      # one autograd node per layer (fused.GINLayerFn); False = one node per kernel (ops.py)
+
     def forward(self, h: Tensor, edge_index: Tensor) -> Tensor:
         # 5 kernels per layer forward: gather(+self term) -> GEMM -> BN+ReLU -> GEMM(+residual h) -> BN+ReLU+dropout
         mlp = self.gin_conv.nn
+        if (self.fused and isinstance(edge_index, Tensor) and h.is_cuda and h.dim() == 2 and h.size(1) % 4 == 0
+                and mlp[1].momentum is not None and self.batch_norm.momentum is not None):
+            graph = graph_of(edge_index, h.size(0))
+            p = DROPOUT_RATE if self.training else 0.0
+            seed = _gnn._dropout_seed() if p > 0.0 else 0
+            prec = ops.PRECISIONS[mlp[0].precision or _gnn.default_precision()]
+            return GINLayerFn.apply(h, self.gin_conv.eps, mlp[0].weight, mlp[0].bias, mlp[1].weight, mlp[1].bias,
+                                    mlp[3].weight, mlp[3].bias, self.batch_norm.weight, self.batch_norm.bias, graph,
+                                    mlp[1], self.batch_norm, self.training, p, seed, prec)
         z = self.gin_conv.aggregate(h, edge_index)
         # (Linear(..., return_stats=True) can hand the BatchNorm statistics over from the GEMM epilogue; measured on
         # C5 it is slower — 265 vs 247 ms/step — because the K=256 GEMMs are epilogue-bound and 76k per-32-row partials
