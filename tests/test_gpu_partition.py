@@ -1,5 +1,5 @@
-"""The node-partitioned path with the real kernels: world size 1 equals the single-device path bit for
-bit; world size 2 over NCCL (needs 2 GPUs, skipped otherwise) reproduces the single-device activations
+"""The node-partitioned path with the real kernels: world size 1 reproduces the single-device path (forward bit
+for bit); world size 2 over NCCL (needs 2 GPUs, skipped otherwise) reproduces the single-device activations
 and gradients of the same graph."""
 import os
 import socket
@@ -56,9 +56,11 @@ def test_world1_partition_equals_single_device():
     l2 = h.sum()
     l2.backward()
     opt.step()
-    assert torch.equal(l1, l2)
+    assert torch.equal(l1, l2)                      # same kernels, same order, same dropout seeds in the forward pass
+    # the partitioned path keeps one autograd node per kernel, the single-device path one per layer: the input
+    # gradient is re-associated (ds + A^T dz + ...), so after one AdamW step the weights agree to rounding
     for (ka, pa), (kb, pb) in zip(step.model.named_parameters(), model.named_parameters()):
-        assert torch.equal(pa, pb), ka
+        torch.testing.assert_close(pa, pb, rtol=0, atol=2e-5, msg=ka)
 
 
 def _worker(rank, world, port, out_dir):
