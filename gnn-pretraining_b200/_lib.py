@@ -43,6 +43,10 @@ SIGNATURES = {
     'gnnb200_lp_features_bwd_f32': [P, I64, P, I64, I64, P, I64, P, P, P, P, I64, P, I64, P],
     'gnnb200_ntxent_fwd_f32': [P, I64, I64, I64, c_float, P, P, P, P, P, SZP, P],
     'gnnb200_ntxent_bwd_f32': [P, P, P, P, I64, I64, c_float, P, I64, P],
+    'gnnb200_normalize_rows_f32': [P, I64, I64, I64, P, P, P],
+    'gnnb200_normalize_rows_bwd_f32': [P, P, I64, P, I64, I64, P, I64, P],
+    'gnnb200_ntxent_sim_fwd_f32': [P, I64, I64, c_float, P, P, P, P],
+    'gnnb200_ntxent_sim_bwd_f32': [P, I64, I64, c_float, P, P, P],
     'gnnb200_pcgrad_f32': [P, P, I64, I64, P, I64, P, P, P, P, P, P, P],
 }
 

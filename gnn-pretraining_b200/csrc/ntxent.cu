@@ -243,9 +243,147 @@ ntx_bwd_kernel(const float* __restrict__ zn, const float* __restrict__ lse, cons
   }
 }
 
+// ---- tensor-core variant: the similarity matrix S = zn zn^T is produced by the tcgen05 GEMM (gemm_tcgen05.cu) and
+// consumed by the two row kernels below (large contrastive batches: the fused FFMA kernel above is O((2M)^2 D) FFMA work) ----
+
+// One warp per row of S [R, R]: lse_i = logsumexp_{j != i}(S_ij / T), loss_i = lse_i - S[i, pos(i)] / T.
+__global__ void __launch_bounds__(256)
+ntx_rows_lse_kernel(const float* __restrict__ S, int64_t lds, int rows, int half, float inv_t, float* __restrict__ lse,
+                    float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= rows) return;
+  const float* row = S + (int64_t)i * lds;
+  float m = -FLT_MAX, s = 0.f;
+  for (int j = lane; j < rows; j += 32) {
+    if (j == i) continue;
+    const float v = row[j] * inv_t;
+    const float nm = fmaxf(m, v);
+    s = s * __expf(m - nm) + __expf(v - nm);
+    m = nm;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = s * __expf(m - nm) + os * __expf(om - nm);
+    m = nm;
+  }
+  if (lane == 0) {
+    const float l = m + logf(s);
+    lse[i] = l;
+    row_loss[i] = l - row[(i + half) % rows] * inv_t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ntx_sum_rows_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float sm[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += v[i];     // fixed strided order
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+// In place: S_ij <- g/T * (exp(S_ij/T - lse_i) - [j == pos(i)]) for j != i, 0 on the diagonal  (= dL/dS_ij).
+__global__ void __launch_bounds__(256)
+ntx_dsim_kernel(float* __restrict__ S, int64_t lds, int rows, int half, float inv_t, const float* __restrict__ lse,
+                const float* __restrict__ grad_loss) {
+  const int64_t total = (int64_t)rows * rows;
+  const float g = (*grad_loss) * inv_t;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(q / rows), j = (int)(q - (int64_t)i * rows);
+    float* p = S + (int64_t)i * lds + j;
+    float w = 0.f;
+    if (j != i) w = g * (__expf(*p * inv_t - lse[i]) - (j == (i + half) % rows ? 1.f : 0.f));
+    *p = w;
+  }
+}
+
+// dz = (dzn - zn * <zn, dzn>) / max(|z|, eps)  (Jacobian of F.normalize); one warp per row.
+__global__ void __launch_bounds__(256)
+ntx_normalize_bwd_kernel(const float* __restrict__ zn, const float* __restrict__ dzn, int64_t ldd,
+                         const float* __restrict__ norm, int rows, int dim, float* __restrict__ dz, int64_t ldz) {
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  float d = 0.f;
+  for (int k = lane; k < dim; k += 32) d = fmaf(zn[(int64_t)r * dim + k], dzn[(int64_t)r * ldd + k], d);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  const float nrm = norm[r];
+  const bool clamped = nrm < kNormEps;
+  const float den = fmaxf(nrm, kNormEps);
+  for (int k = lane; k < dim; k += 32) {
+    const float g = dzn[(int64_t)r * ldd + k];
+    dz[(int64_t)r * ldz + k] = (clamped ? g : (g - zn[(int64_t)r * dim + k] * d)) / den;
+  }
+}
+
 }  // namespace gnnb200
 
 using namespace gnnb200;
+
+extern "C" int gnnb200_normalize_rows_f32(const float* z, int64_t ldz, int64_t rows, int64_t dim, float* zn, float* norm,
+                                          gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows < 0 || dim < 0) return GNNB200_EINVAL;
+  if (rows == 0 || dim == 0) return GNNB200_OK;
+  if (!z || !zn || !norm) return GNNB200_EINVAL;
+  ntx_normalize_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(z, ldz, (int)rows, (int)dim, zn, norm);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+extern "C" int gnnb200_normalize_rows_bwd_f32(const float* zn, const float* grad_zn, int64_t ldg, const float* norm,
+                                              int64_t rows, int64_t dim, float* grad_z, int64_t ldz,
+                                              gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows < 0 || dim < 0) return GNNB200_EINVAL;
+  if (rows == 0 || dim == 0) return GNNB200_OK;
+  if (!zn || !grad_zn || !norm || !grad_z) return GNNB200_EINVAL;
+  ntx_normalize_bwd_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(zn, grad_zn, ldg, norm, (int)rows,
+                                                                                   (int)dim, grad_z, ldz);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+extern "C" int gnnb200_ntxent_sim_fwd_f32(const float* sim, int64_t lds, int64_t two_m, float temperature, float* lse,
+                                          float* row_loss, float* loss, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (two_m < 0 || (two_m & 1)) return GNNB200_EINVAL;
+  if (two_m >= (1 << 24)) return GNNB200_ERANGE;
+  if (!loss || (two_m > 0 && (!sim || !lse || !row_loss)) || !(temperature > 0.f)) return GNNB200_EINVAL;
+  if (two_m > 0) {
+    ntx_rows_lse_kernel<<<(unsigned)((two_m * 32 + 255) / 256), 256, 0, stream>>>(sim, lds, (int)two_m, (int)(two_m / 2),
+                                                                                 1.0f / temperature, lse, row_loss);
+    GNNB200_LAUNCH_CHECK();
+  }
+  ntx_sum_rows_kernel<<<1, 256, 0, stream>>>(row_loss, (int)two_m, loss);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+extern "C" int gnnb200_ntxent_sim_bwd_f32(float* sim, int64_t lds, int64_t two_m, float temperature, const float* lse,
+                                          const float* grad_loss, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (two_m < 0 || (two_m & 1)) return GNNB200_EINVAL;
+  if (two_m == 0) return GNNB200_OK;
+  if (two_m >= (1 << 24)) return GNNB200_ERANGE;
+  if (!sim || !lse || !grad_loss || !(temperature > 0.f)) return GNNB200_EINVAL;
+  int64_t blocks = (two_m * two_m + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  ntx_dsim_kernel<<<(unsigned)blocks, 256, 0, stream>>>(sim, lds, (int)two_m, (int)(two_m / 2), 1.0f / temperature, lse,
+                                                        grad_loss);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
 
 extern "C" int gnnb200_ntxent_fwd_f32(const float* z, int64_t ldz, int64_t two_m, int64_t dim, float temperature,
                                       float* zn, float* lse, float* norm, float* loss, void* workspace,

@@ -71,7 +71,8 @@ KERNELS_PER_CALL = {
     'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_colstats_f32': 2,
     'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
-    'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2,
+    'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
+    'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,
 }
 _calls = {}
 AGG_TIMER = None      # bench.py sets this to a list to collect (start, stop) CUDA events per aggregation launch
@@ -896,6 +897,102 @@ def _ntx_backward(ctx, g_loss, g_zn, g_lse, g_norm):
 
 
 ntxent_fwd.register_autograd(_ntx_backward, setup_context=_ntx_setup)
+
+
+# ---- tensor-core NT-Xent: similarity matrix on tcgen05, row reductions around it ----------------------------
+@_op('normalize_rows')
+def normalize_rows(z: Tensor) -> Tuple[Tensor, Tensor]:
+    """(z / max(|z|, 1e-12) row-wise, |z|) = F.normalize(z, dim=1) and the norms."""
+    _need_cuda(z)
+    z = _rowmajor(z)
+    zn = torch.empty(z.size(0), z.size(1), dtype=torch.float32, device=z.device)
+    norm = torch.empty(z.size(0), dtype=torch.float32, device=z.device)
+    L.check(_invoke('gnnb200_normalize_rows_f32', _ptr(z), _ld(z), z.size(0), z.size(1), _ptr(zn), _ptr(norm), _stream(z)),
+            'normalize_rows')
+    return zn, norm
+
+
+@normalize_rows.register_fake
+def _(z):
+    return torch.empty_like(z), z.new_empty(z.size(0))
+
+
+@_op('normalize_rows_bwd')
+def normalize_rows_bwd(zn: Tensor, grad_zn: Tensor, norm: Tensor) -> Tensor:
+    _need_cuda(zn, grad_zn, norm)
+    g = _rowmajor(grad_zn)
+    out = torch.empty_like(zn)
+    L.check(_invoke('gnnb200_normalize_rows_bwd_f32', _ptr(zn), _ptr(g), _ld(g), _ptr(norm), zn.size(0), zn.size(1),
+                    _ptr(out), _ld(out), _stream(zn)), 'normalize_rows_bwd')
+    return out
+
+
+@normalize_rows_bwd.register_fake
+def _(zn, grad_zn, norm):
+    return torch.empty_like(zn)
+
+
+@_op('ntxent_sim_fwd')
+def ntxent_sim_fwd(sim: Tensor, temperature: float) -> Tuple[Tensor, Tensor]:
+    """(loss [1], lse [2M]) from the similarity matrix sim = zn zn^T [2M, 2M] (diagonal excluded, positives i <-> i+M)."""
+    _need_cuda(sim)
+    sim = _rowmajor(sim)
+    R = sim.size(0)
+    lse = torch.empty(R, dtype=torch.float32, device=sim.device)
+    row_loss = torch.empty(max(R, 1), dtype=torch.float32, device=sim.device)
+    loss = torch.empty(1, dtype=torch.float32, device=sim.device)
+    L.check(_invoke('gnnb200_ntxent_sim_fwd_f32', _ptr(sim), _ld(sim), R, temperature, _ptr(lse), _ptr(row_loss), _ptr(loss),
+                    _stream(sim)), 'ntxent_sim_fwd')
+    return loss, lse
+
+
+@ntxent_sim_fwd.register_fake
+def _(sim, temperature):
+    return sim.new_empty(1), sim.new_empty(sim.size(0))
+
+
+@_op('ntxent_sim_bwd_', mutates=('sim',))
+def ntxent_sim_bwd_(sim: Tensor, temperature: float, lse: Tensor, grad_loss: Tensor) -> None:
+    """Overwrite sim in place with dL/dsim."""
+    _need_cuda(sim, lse, grad_loss)
+    if sim.stride(1) != 1:
+        raise L.Gnnb200Error('sim must be row-major')
+    gl = grad_loss.contiguous().view(1)
+    L.check(_invoke('gnnb200_ntxent_sim_bwd_f32', _ptr(sim), _ld(sim), sim.size(0), temperature, _ptr(lse), _ptr(gl),
+                    _stream(sim)), 'ntxent_sim_bwd')
+
+
+@ntxent_sim_bwd_.register_fake
+def _(sim, temperature, lse, grad_loss):
+    return None
+
+
+class _NtXentTensorCore(torch.autograd.Function):
+    """NT-Xent with the [2M, 2M] similarity matrix formed on the tensor cores (three tcgen05 GEMMs per step: sim,
+    dsim*zn, dsim^T*zn); the matrix lives only between forward and backward and is overwritten by its own gradient."""
+
+    @staticmethod
+    def forward(ctx, z: Tensor, temperature: float, precision: int):
+        zn, norm = normalize_rows.fn(z)
+        sim = _gemm_raw(zn, False, zn, True, None, False, precision)
+        loss, lse = ntxent_sim_fwd.fn(sim, float(temperature))
+        ctx.saved = (zn, norm, sim, lse)
+        ctx.cfg = (float(temperature), precision)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss: Tensor):
+        zn, norm, sim, lse = ctx.saved
+        temperature, precision = ctx.cfg
+        ntxent_sim_bwd_.fn(sim, temperature, lse, g_loss)
+        gzn = _gemm_raw(sim, False, zn, False, None, False, precision)
+        gzn = _gemm_raw(sim, True, zn, False, None, False, precision, gzn)       # + dsim^T zn in the epilogue
+        ctx.saved = None
+        return normalize_rows_bwd.fn(zn, gzn, norm), None, None
+
+
+def ntxent_tensor_core(z: Tensor, temperature: float, precision: int) -> Tensor:
+    return _NtXentTensorCore.apply(z, temperature, precision)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -68,12 +68,27 @@ class GRLScheduler:
         self.current_step += 1
 
 
+# 2M at or above this takes the tensor-core path: sim = zn zn^T on tcgen05 (materialised once, overwritten by its own
+# gradient) instead of the fused FFMA kernel that never materialises it.  The FFMA kernel is exact-fp32 and memory-free
+# but O((2M)^2 D) scalar work; the crossover on B200 is around a few thousand rows.
+NTXENT_TENSOR_CORE_ROWS = 2048
+NTXENT_TENSOR_CORE_MAX_ROWS = 46000          # 8.5 GB of fp32 similarities
+
+
 def nt_xent(z1: Tensor, z2: Tensor, temperature: float) -> Tuple[Tensor, Tensor]:
-    """reference tasks.py:192-213 / :265-287 as one fused kernel pair: normalise, tiled
-    similarity with online log-sum-exp (diagonal excluded), CE(sum) against the paired view."""
+    """reference tasks.py:192-213 / :265-287: normalise, similarity / T with the diagonal excluded, CE(sum) against
+    the paired view.  Small batches: one fused kernel pair (tiled similarity + online log-sum-exp, fp32 FFMA); large
+    batches: similarity and its two backward contractions as tcgen05 GEMMs."""
+    from . import nn as _gnn
     m = z1.size(0)
-    loss, _, _, _ = ops.ntxent_fwd(torch.cat([z1, z2], dim=0), float(temperature))
-    return loss.squeeze(0), torch.tensor(2 * m, device=z1.device, dtype=torch.long)
+    z = torch.cat([z1, z2], dim=0)
+    size = torch.tensor(2 * m, device=z1.device, dtype=torch.long)
+    prec = _gnn.default_precision()
+    if NTXENT_TENSOR_CORE_ROWS <= 2 * m <= NTXENT_TENSOR_CORE_MAX_ROWS and prec != 'f32' and z.size(1) % 4 == 0:
+        loss = ops.ntxent_tensor_core(z, float(temperature), ops.PRECISIONS[prec])
+        return loss.squeeze(0), size
+    loss, _, _, _ = ops.ntxent_fwd(z, float(temperature))
+    return loss.squeeze(0), size
 
 
 def _num_graphs(batch) -> int:

@@ -207,6 +207,18 @@ int gnnb200_ntxent_bwd_f32(const float* zn, const float* lse, const float* norm,
                            int64_t two_m, int64_t dim, float temperature, float* grad_z, int64_t ldgz,
                            gnnb200_stream_t stream);
 
+/* Tensor-core variant of the same loss for large contrastive batches: the caller forms sim = zn zn^T [2M, 2M] with
+ * gnnb200_gemm_f32 (tcgen05), sim_fwd reduces it row-wise (lse, per-row loss, total loss), sim_bwd overwrites it IN PLACE
+ * with dL/dsim, and grad_zn = (dsim + dsim^T) zn is two more GEMMs; normalize_rows(_bwd) are F.normalize and its Jacobian. */
+int gnnb200_normalize_rows_f32(const float* z, int64_t ldz, int64_t rows, int64_t dim, float* zn, float* norm,
+                               gnnb200_stream_t stream);
+int gnnb200_normalize_rows_bwd_f32(const float* zn, const float* grad_zn, int64_t ldg, const float* norm, int64_t rows,
+                                   int64_t dim, float* grad_z, int64_t ldz, gnnb200_stream_t stream);
+int gnnb200_ntxent_sim_fwd_f32(const float* sim, int64_t lds, int64_t two_m, float temperature, float* lse,
+                               float* row_loss, float* loss, gnnb200_stream_t stream);
+int gnnb200_ntxent_sim_bwd_f32(float* sim, int64_t lds, int64_t two_m, float temperature, const float* lse,
+                               const float* grad_loss, gnnb200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Gradient surgery on a flat buffer (src/pretrain/gradient_surgery.py:41-101).
  * task_grads [T, P] holds each task's gradient of every parameter (zeros where absent); the P

@@ -113,3 +113,38 @@ def test_dot_is_deterministic_and_accurate():
     assert torch.equal(d1, d2)
     want = float((a.double() * b.double()).sum())
     assert abs(float(d1) - want) < 1e-4 * max(1.0, abs(want)) + 0.05
+
+
+@pytest.mark.parametrize('m,d', [(64, 128), (300, 128), (1500, 128), (700, 64)])
+@pytest.mark.parametrize('prec,tol', [('tf32x3_strict', 2e-5), ('tf32_strict', 5e-3)])
+def test_ntxent_tensor_core_path(m, d, prec, tol):
+    """Similarity matrix and its two backward contractions on tcgen05 (tasks.nt_xent takes this path for 2M >= 2048)."""
+    g = torch.Generator().manual_seed(m * 3 + d)
+    z1 = torch.randn(m, d, generator=g)
+    z2 = z1 + 0.3 * torch.randn(m, d, generator=g)
+    a = torch.cat([z1, z2]).requires_grad_(True)
+    lo, _ = orc.nt_xent(a[:m], a[m:], 0.3)
+    lo.backward()
+    b = torch.cat([z1, z2]).to(DEV).requires_grad_(True)
+    lg = ops.ntxent_tensor_core(b, 0.3, ops.PRECISIONS[prec])
+    lg.backward()
+    assert abs(float(lg) - float(lo)) < tol * abs(float(lo))
+    scale = a.grad.abs().max()
+    assert float((b.grad.cpu() - a.grad).abs().max() / scale) < max(tol * 5, 1e-4)
+
+
+def test_nt_xent_dispatches_by_size():
+    from gnnb200 import nn as gnn
+    old = gnn.default_precision()
+    try:
+        gnn.set_default_precision('tf32x3')
+        g = torch.Generator().manual_seed(0)
+        z1, z2 = torch.randn(1100, 128, generator=g), torch.randn(1100, 128, generator=g)
+        lo, so = orc.nt_xent(z1, z2, 0.5)
+        before = dict(ops.call_counts())
+        lg, sg = tasks.nt_xent(z1.to(DEV), z2.to(DEV), 0.5)
+        after = ops.call_counts()
+        assert after.get('gnnb200_ntxent_sim_fwd_f32', 0) == before.get('gnnb200_ntxent_sim_fwd_f32', 0) + 1   # tensor path
+        assert int(sg) == int(so) and abs(float(lg) - float(lo)) < 2e-5 * abs(float(lo))
+    finally:
+        gnn.set_default_precision(old)
