@@ -16,6 +16,7 @@ destination ranges with an NCCL all-gather of the layer input per layer ("strong
 PyG shim) on a bounded node/edge sample of the same workload with all host threads.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -148,7 +149,8 @@ def run_product(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # short collective timeout: a mismatched collective must abort the run, not hold 8 GPUs for ten minutes
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     import gnnb200  # noqa: F401
     from gnnb200 import models as prod, ops
     from gnnb200 import nn as gnn
@@ -458,7 +460,7 @@ def run_c4(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     import gnnb200  # noqa: F401
     from gnnb200 import data as data_mod, models, partition, synthetic, tasks as task_mod
     from gnnb200.gradient_surgery import GradientSurgery

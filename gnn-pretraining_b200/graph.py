@@ -20,13 +20,14 @@ class Graph:
         self.edge_index = edge_index
         self.num_nodes = int(num_nodes)
         self.num_edges = int(edge_index.size(1))
-        self.rowptr, self.col, self.eid = ops.csr_build(edge_index, self.num_nodes, False)
+        self.rowptr, self.col, _ = ops.csr_build(edge_index, self.num_nodes, False)   # the edge permutation is not kept
         self._t = None
         self._version = edge_index._version
 
     def transposed(self):
         if self._t is None:
-            self._t = ops.csr_build(self.edge_index, self.num_nodes, True)
+            rowptr_t, col_t, _ = ops.csr_build(self.edge_index, self.num_nodes, True)
+            self._t = (rowptr_t, col_t)
         return self._t
 
     @property

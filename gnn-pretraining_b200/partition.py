@@ -204,16 +204,34 @@ class partition_scope:
 
 
 def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
-    """One flat all-reduce (sum) over every parameter gradient (C1 of SURVEY §2.4)."""
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
-    if not grads:
+    """One flat all-reduce (sum) over every parameter gradient (C1 of SURVEY §2.4).
+
+    Every rank contributes a buffer with the SAME layout — all parameters in `module.parameters()` order, zeros
+    where this rank has no gradient — because which parameters carry a gradient can differ between replicas (the
+    reference's gradient surgery only writes the parameters of the first task of an unseeded shuffle,
+    src/pretrain/gradient_surgery.py:43,60-68).  A parameter ends up with a gradient iff some rank had one (its
+    presence flags travel in the same buffer); the others keep `.grad = None`, so the optimizer skips them exactly as
+    it would on one device."""
+    params = list(module.parameters())
+    if not params:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    dev = params[0].device
+    pieces = [(p.grad.reshape(-1) if p.grad is not None else torch.zeros(p.numel(), dtype=torch.float32, device=dev))
+              for p in params]
+    flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=torch.float32, device=dev)
+    flat = torch.cat(pieces + [flags])
     dist.all_reduce(flat, group=group)
+    have = (flat[-len(params):] > 0).tolist()                    # one small device->host read
     off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+    for p, present in zip(params, have):
+        n = p.numel()
+        if present:
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+        off += n
 
 
 class PartitionedBackboneStep:

@@ -107,6 +107,21 @@ def _worker(rank, world, port, n, e, f, out_dir):
         partition.allreduce_gradients(lin)
         assert torch.equal(lin.weight.grad, torch.full_like(lin.weight, float(sum(range(1, world + 1)))))
         assert torch.equal(lin.bias.grad, torch.full_like(lin.bias, 10.0 * sum(range(1, world + 1))))
+
+        # ---- replicas disagree on WHICH parameters carry a gradient (gradient surgery writes only the first shuffled
+        #      task's parameters, reference gradient_surgery.py:60-68): same wire layout on every rank, union of owners ----
+        net = torch.nn.ModuleDict({'a': torch.nn.Linear(3, 2), 'b': torch.nn.Linear(2, 2), 'c': torch.nn.Linear(2, 1)})
+        owners = {'a': (0, 1), 'b': (0,), 'c': ()}               # a: both ranks, b: rank 0 only, c: nobody
+        for name, mod in net.items():
+            for p in mod.parameters():
+                p.grad = torch.full_like(p, float(rank + 1)) if rank in owners[name] else None
+        partition.allreduce_gradients(net)
+        for p in net['a'].parameters():
+            assert torch.equal(p.grad, torch.full_like(p, 3.0))
+        for p in net['b'].parameters():
+            assert torch.equal(p.grad, torch.full_like(p, 1.0))    # rank 1 had none: receives rank 0's
+        for p in net['c'].parameters():
+            assert p.grad is None                                  # nobody had one: the optimizer keeps skipping it
         open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
     finally:
         dist.destroy_process_group()
