@@ -57,10 +57,22 @@ def test_world1_partition_equals_single_device():
     l2.backward()
     opt.step()
     assert torch.equal(l1, l2)                      # same kernels, same order, same dropout seeds in the forward pass
-    # the partitioned path keeps one autograd node per kernel, the single-device path one per layer: the input
-    # gradient is re-associated (ds + A^T dz + ...), so after one AdamW step the weights agree to rounding
+    # The partitioned path keeps one autograd node per kernel, the single-device path one per layer whose transposed
+    # gather continues the residual gradient's buffer: dh = (ds + A^T dz) + (1+eps) dz versus ds + (A^T dz + (1+eps) dz).
+    # Gradients therefore agree to fp32 re-association, not bitwise.  The weights after the AdamW step are NOT a
+    # rounding-level check (Adam's first update is lr * g / (|g| + 1e-8) ~ +-lr, so an element whose near-zero gradient
+    # changes sign moves by 2 lr): they are only bounded by that.
+    lr = 1e-4
     for (ka, pa), (kb, pb) in zip(step.model.named_parameters(), model.named_parameters()):
-        torch.testing.assert_close(pa, pb, rtol=0, atol=2e-5, msg=ka)
+        assert ka == kb
+        ga, gb, pa, pb = pa.grad, pb.grad, pa.detach(), pb.detach()
+        assert (ga is None) == (gb is None), ka
+        err, ref = float((ga - gb).norm()), float(gb.norm())
+        # measured on B200 (tf32 GEMMs): <= 1.7e-4 for the weights of layers 0/1 and the encoder, 0 for the last layer
+        tol = 5e-2 if ka.endswith('eps') else 1e-3          # d(eps) is one cancelling dot product over all rows
+        print(f'{ka}: |dg| = {err:.3e}, |g| = {ref:.3e}, max |dw| = {float((pa - pb).abs().max()):.3e}')
+        assert err <= tol * ref + 1e-7, (ka, err, ref)
+        assert float((pa - pb).abs().max()) <= 2 * lr * 1.01, ka
 
 
 def _worker(rank, world, port, out_dir):
