@@ -164,7 +164,7 @@ def run_product(args):
 
     if world > 1:
         from gnnb200 import partition
-        runner = partition.PartitionedBackboneStep(prod, dev, C5_F, HIDDEN, LAYERS, n, rank, world)
+        runner = partition.PartitionedBackboneStep(prod, dev, C5_F, HIDDEN, LAYERS, n, rank, world, halo=args.halo)
         one_step = lambda x, ei, local=False: runner.step(x, ei, local)  # noqa: E731
     else:
         model = build_model(prod, dev, C5_F)
@@ -293,7 +293,8 @@ def run_product(args):
                        'hidden': HIDDEN, 'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
                        'edge_locality': args.locality, 'gemm_precision': gnn.default_precision(),
                        'l2_policy': 'inputs_larger_than_L2 (2.5 GB activations per layer vs 126 MB L2)',
-                       'parallelism': 'single' if world == 1 else f'node_partition{world}+halo_allgather'},
+                       'parallelism': 'single' if world == 1 else f'node_partition{world}+' + (
+                           'halo_alltoall_sparse' if runner.last_halo == 'sparse' else 'halo_allgather')},
             'clocks': clocks.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4,
@@ -586,6 +587,8 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C5 graph (debug only; 1.0 = BASELINE config)')
     ap.add_argument('--locality', type=float, default=0.0, help='fraction of intra-block edges (0 = uniform random)')
     ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3'])
+    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'auto'],
+                    help='N > 1: rows exchanged per layer (default dense = all-gather; see gnnb200/partition.py)')
     ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')

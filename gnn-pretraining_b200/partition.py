@@ -31,6 +31,22 @@ from . import ops
 # the local gather is longer than the exchange (few ranks, high-degree graphs); it stays opt-in.
 DEFAULT_HALO_CHUNKS = 1
 
+# Which rows travel per layer and direction ("halo = all remote rows for the uniform generator; only
+# referenced blocks for the locality generator"):
+#   'dense'  : all-gather of every rank's whole shard (each row crosses NVLink once, no index traffic, no packing);
+#              right when nearly every remote row is referenced — on the uniform-random C5 graph a rank touches
+#              ~96 % of all rows at 8 ranks.  The measured default.
+#   'sparse' : each rank receives only the remote rows its edges reference: the needed ids are exchanged once per
+#              graph (HaloPlan), then per layer the owners pack those rows (rows_gather kernel) and one
+#              all_to_all_single with uneven splits delivers them behind the rank's own rows in one buffer
+#              [n_local + halo, F] that the local CSR indexes.  Same per-row edge order => same bits as 'dense'.
+#   'auto'   : 'sparse' iff the largest needed fraction of remote rows over all ranks is below
+#              SPARSE_HALO_MAX_FRACTION (one small all-reduce per graph, so every rank takes the same branch).
+# 'sparse'/'auto' are covered by the gloo world-2 tests (index plan, exchange, algebra) but were written after the
+# round's GPU budget was spent: unmeasured on NCCL, hence opt-in (GNNB200_HALO or the `halo=` argument).
+DEFAULT_HALO = 'dense'
+SPARSE_HALO_MAX_FRACTION = 0.5
+
 
 def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
     """(lo, hi, rows_per_rank) of the contiguous equal split; the last rank may own fewer rows."""
@@ -38,6 +54,53 @@ def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
     lo = min(num_nodes, rank * per)
     hi = min(num_nodes, lo + per)
     return lo, hi, per
+
+
+def _pack_rows(x_local: Tensor, idx: Tensor) -> Tensor:
+    """Rows of this rank's shard that the peers asked for, in request order (the send buffer of the sparse exchange)."""
+    return ops.rows_gather.fn(x_local, idx)
+
+
+class HaloPlan:
+    """One direction's sparse halo of one rank: which remote rows its owned edges reference (`need`, ascending global
+    ids, hence grouped by owner), which of its own rows every peer references (`serve_idx`, local ids, grouped by
+    requesting rank), and the owned edges' column endpoints renumbered into the exchange buffer
+    [own rows 0..n_local) | halo rows n_local..n_local+H)`.  Built once per graph with two small all-to-alls
+    (counts, then ids)."""
+
+    def __init__(self, other: Tensor, lo: int, hi: int, per: int, world: int, group=None):
+        self.n_local, self.group = hi - lo, group
+        remote = (other < lo) | (other >= hi)
+        need = torch.unique(other[remote])                              # sorted => grouped by owner rank
+        owner = torch.div(need, per, rounding_mode='floor')
+        need_cnt = torch.bincount(owner, minlength=world)
+        serve_cnt = torch.empty_like(need_cnt)
+        dist.all_to_all_single(serve_cnt, need_cnt, group=group)
+        self.need_cnt, self.serve_cnt = need_cnt.tolist(), serve_cnt.tolist()    # one host read each, per graph
+        self.serve_idx = need.new_empty(sum(self.serve_cnt))
+        dist.all_to_all_single(self.serve_idx, need - owner * per, output_split_sizes=self.serve_cnt,
+                               input_split_sizes=self.need_cnt, group=group)
+        self.halo_rows = int(need.numel())
+        self.col = torch.where(remote, self.n_local + torch.searchsorted(need, other), other - lo)
+
+    def exchange(self, x_local: Tensor) -> Tensor:
+        """[n_local + H, F]: this rank's rows followed by the remote rows it references (ascending global id)."""
+        f = x_local.size(1)
+        buf = x_local.new_empty(self.n_local + self.halo_rows, f)
+        buf[: self.n_local].copy_(x_local[: self.n_local])
+        send = _pack_rows(x_local, self.serve_idx)
+        dist.all_to_all_single(buf[self.n_local:], send, output_split_sizes=self.need_cnt,
+                               input_split_sizes=self.serve_cnt, group=self.group)
+        return buf
+
+
+def remote_fraction_needed(other: Tensor, lo: int, hi: int, num_nodes: int, group=None) -> float:
+    """max over ranks of (distinct remote rows referenced) / (remote rows): the 'auto' criterion."""
+    remote = (other < lo) | (other >= hi)
+    frac = torch.unique(other[remote]).numel() / max(1, num_nodes - (hi - lo))
+    t = torch.tensor([frac], dtype=torch.float32, device=other.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t)
 
 
 class PartitionedGraph:
@@ -52,9 +115,14 @@ class PartitionedGraph:
     from pass to pass in a fixed order (piece 0 edges in edge order, then piece 1, ...), so results are
     deterministic; they differ from the single-device edge order only by fp32 re-association."""
 
-    def __init__(self, edge_index: Tensor, num_nodes: int, rank: int, world: int, group=None, chunks: Optional[int] = None):
+    def __init__(self, edge_index: Tensor, num_nodes: int, rank: int, world: int, group=None, chunks: Optional[int] = None,
+                 halo: Optional[str] = None):
         if chunks is None:
             chunks = int(os.environ.get('GNNB200_HALO_CHUNKS', DEFAULT_HALO_CHUNKS))
+        if halo is None:
+            halo = os.environ.get('GNNB200_HALO', DEFAULT_HALO)
+        if halo not in ('dense', 'sparse', 'auto'):
+            raise ValueError(f'halo must be dense, sparse or auto, not {halo!r}')
         self.num_nodes, self.rank, self.world, self.group = int(num_nodes), rank, world, group
         self.lo, self.hi, self.per = shard_bounds(self.num_nodes, rank, world)
         self.n_local = self.hi - self.lo
@@ -62,8 +130,28 @@ class PartitionedGraph:
         self.rpc = (self.per + self.chunks - 1) // self.chunks            # rows per piece of one shard
         n_rows = max(self.n_local, 1)
         src, dst = edge_index[0], edge_index[1]
+        if world > 1 and halo == 'auto':
+            own = (dst >= self.lo) & (dst < self.hi)
+            frac = remote_fraction_needed(src[own], self.lo, self.hi, self.num_nodes, group)
+            halo = 'sparse' if frac < SPARSE_HALO_MAX_FRACTION else 'dense'
+        self.halo = halo if world > 1 else 'dense'
+        self.plan = self.plan_t = None
+        if self.halo == 'sparse':
+            self.chunks = 1
+            self.rowptr, self.col, self.local_edges, self.plan = self._build_sparse(src, dst, n_rows)
+            self.rowptr_t, self.col_t, _, self.plan_t = self._build_sparse(dst, src, n_rows)
+            return
         self.rowptr, self.col, self.local_edges = self._build(src, dst, n_rows)       # own destinations
         self.rowptr_t, self.col_t, _ = self._build(dst, src, n_rows)                  # own sources (transposed)
+
+    def _build_sparse(self, other: Tensor, mine: Tensor, n_rows: int):
+        """CSR over the owned edges whose columns index the sparse exchange buffer (HaloPlan)."""
+        own = (mine >= self.lo) & (mine < self.hi)
+        plan = HaloPlan(other[own], self.lo, self.hi, self.per, self.world, self.group)
+        m = mine[own] - self.lo
+        rowptr, col, _ = ops.csr_build(torch.stack([plan.col, m], dim=0), n_rows, False)
+        plan.col = None                                                   # only the CSR copy is kept
+        return rowptr, col, int(m.numel()), plan
 
     def _build(self, other: Tensor, mine: Tensor, n_rows: int):
         """Sub-CSRs over the edges whose `mine` endpoint this rank owns; columns = `other` endpoints."""
@@ -119,6 +207,9 @@ class PartitionedGraph:
         rowptr, col = (self.rowptr_t, self.col_t) if transposed else (self.rowptr, self.col)
         if self.world == 1:
             return ops._aggregate_raw(x_local, rowptr, col, L.AGG_SUM, x_local, eps, None)
+        if self.halo == 'sparse':
+            buf = (self.plan_t if transposed else self.plan).exchange(x_local)
+            return ops._aggregate_raw(buf, rowptr, col, L.AGG_SUM, x_local, eps, None)
         pieces = self.gather_pieces_async(x_local)
         out = None
         for c, (work, buf) in enumerate(pieces):
@@ -239,17 +330,19 @@ class PartitionedBackboneStep:
     rank's shard.  Every rank builds the same model from the same seed."""
 
     def __init__(self, models, device, feat_in: int, hidden: int, layers: int, num_nodes: int, rank: int,
-                 world: int, group=None, seed: int = 0, lr: float = 1e-4):
+                 world: int, group=None, seed: int = 0, lr: float = 1e-4, halo: Optional[str] = None):
         torch.manual_seed(seed)
         self.model = torch.nn.ModuleDict({'input_encoder': models.InputEncoder(feat_in, hidden),
                                           'gnn_backbone': models.GINBackbone(layers, hidden)}).to(device)
         self.model.train()
         self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr)
         self.num_nodes, self.rank, self.world, self.group = num_nodes, rank, world, group
+        self.halo, self.last_halo = halo, None
 
     def step(self, x: Tensor, edge_index: Tensor, x_is_local: bool = False) -> Tensor:
         """x: the full [N, F] feature matrix, or (x_is_local) just this rank's row shard."""
-        graph = PartitionedGraph(edge_index, self.num_nodes, self.rank, self.world, self.group)
+        graph = PartitionedGraph(edge_index, self.num_nodes, self.rank, self.world, self.group, halo=self.halo)
+        self.last_halo = graph.halo
         x_local = x if x_is_local else x[graph.lo:graph.hi]
         self.opt.zero_grad(set_to_none=True)
         with partition_scope(graph):

@@ -118,3 +118,36 @@ def _worker(rank, world, port, out_dir):
 def test_world2_nccl_matches_single_device(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(2))
+
+
+def _sparse_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        n, e = 6001, 80000
+        data = synthetic.products_like(n, e, 100, seed=2, locality=0.9, blocks=16, device=dev)
+        x = torch.randn(n, 256, generator=torch.Generator().manual_seed(4)).to(dev)
+        eps = torch.tensor([0.25], device=dev)
+        dense = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='dense', chunks=1)
+        sparse = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='sparse')
+        auto = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='auto')
+        assert sparse.halo == 'sparse' and sparse.plan.halo_rows < n - sparse.n_local
+        for transposed in (False, True):
+            a = dense.aggregate(x[dense.lo:dense.hi].contiguous(), eps, transposed)
+            b = sparse.aggregate(x[sparse.lo:sparse.hi].contiguous(), eps, transposed)
+            c = auto.aggregate(x[auto.lo:auto.hi].contiguous(), eps, transposed)
+            assert torch.equal(a, b) and torch.equal(a, c)          # same edge order per row => same bits
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+@pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
+                    reason='sparse halo exchange: host logic verified over gloo (tests/test_partition_gloo.py); the NCCL leg was '
+                           'written after the round-1 GPU budget was spent — set GNNB200_RUN_UNVERIFIED=1 to run it')
+def test_world2_sparse_halo_equals_dense(tmp_path):
+    mp.spawn(_sparse_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(2))

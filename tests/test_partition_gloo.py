@@ -127,6 +127,60 @@ def _worker(rank, world, port, n, e, f, out_dir):
         dist.destroy_process_group()
 
 
+def _sparse_worker(rank, world, port, n, e, f, locality, out_dir):
+    """Sparse halo exchange (partition.HaloPlan): only referenced remote rows travel, delivered behind the rank's own rows;
+    the renumbered CSR over that buffer gives the same rows — bit for bit — as the CSR over the all-gathered matrix."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    partition._pack_rows = lambda x, idx: x.index_select(0, idx)        # CPU stand-in for the rows_gather kernel
+    try:
+        from gnnb200 import synthetic
+        d = synthetic.products_like(n, e, f, seed=7, locality=locality, blocks=8)
+        ei, x = d['edge_index'], d['x']
+        gout = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+        eps = torch.tensor([0.3])
+        lo, hi, per = partition.shard_bounds(n, rank, world)
+        n_local = hi - lo
+        for mine_row, other_row, feat in ((1, 0, x), (0, 1, gout)):        # forward (own dst), transposed (own src)
+            mine, other = ei[mine_row], ei[other_row]
+            own = (mine >= lo) & (mine < hi)
+            o, m = other[own], mine[own] - lo
+            plan = partition.HaloPlan(o, lo, hi, per, world)
+            # -- the plan: needed ids are exactly the distinct remote endpoints; every peer serves what was asked of it
+            remote = (o < lo) | (o >= hi)
+            want = torch.unique(o[remote])
+            assert plan.halo_rows == want.numel() and sum(plan.need_cnt) == want.numel() and plan.need_cnt[rank] == 0
+            assert plan.serve_cnt[rank] == 0 and plan.serve_idx.numel() == sum(plan.serve_cnt)
+            assert bool(((plan.serve_idx >= 0) & (plan.serve_idx < n_local)).all())
+            assert bool(((plan.col >= 0) & (plan.col < n_local + plan.halo_rows)).all())
+            # -- the exchange delivers own rows, then the needed remote rows in ascending global id
+            buf = plan.exchange(feat[lo:hi])
+            assert torch.equal(buf[:n_local], feat[lo:hi]) and torch.equal(buf[n_local:], feat[want])
+            assert torch.equal(buf[plan.col], feat[o])                   # every owned edge finds its endpoint's row
+            # -- same CSR order over the renumbered columns => identical sums to the dense (all-gather) exchange
+            rp, col_sparse = _csr(m, plan.col, max(n_local, 1))
+            _, col_dense = _csr(m, o, max(n_local, 1))
+            z_sparse = _oracle_agg(buf, rp, col_sparse, feat[lo:hi], eps)
+            z_dense = _oracle_agg(feat, rp, col_dense, feat[lo:hi], eps)
+            assert torch.equal(z_sparse, z_dense)
+            # -- the 'auto' criterion is the same number on every rank
+            frac = partition.remote_fraction_needed(o, lo, hi, n)
+            every = [None] * world
+            dist.all_gather_object(every, frac)
+            assert len(set(every)) == 1 and 0.0 <= frac <= 1.0
+            if locality >= 0.9 and world > 1:
+                assert frac < 0.9                                        # a graph with locality needs a strict subset
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,e,locality', [(2, 101, 700, 0.0), (3, 101, 400, 0.95), (2, 7, 5, 0.0), (3, 2, 6, 0.0)])
+def test_sparse_halo_plan_and_exchange(tmp_path, world, n, e, locality):
+    mp.spawn(_sparse_worker, args=(world, _free_port(), n, e, 8, locality, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
 @pytest.mark.parametrize('n,e', [(101, 700), (64, 300)])
 def test_partition_algebra_world2(tmp_path, n, e):
     world = 2
