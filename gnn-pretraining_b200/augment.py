@@ -108,7 +108,9 @@ class GraphAugmentor:
         ptr = getattr(batch, '_ptr_host', None)
         if ptr is None:
             ptr = batch.ptr.tolist()
-        ei = batch.edge_index.cpu().numpy()                 # one transfer; every per-graph decision is host arithmetic
+        ei = getattr(batch, '_edge_index_host', None)       # host mirror kept by gnnb200.loader: no device read-back
+        if ei is None:
+            ei = batch.edge_index.cpu().numpy()             # one transfer; every per-graph decision is host arithmetic
         # edges of graph g are the columns whose source lies in [ptr[g], ptr[g+1]) (PyG batches keep them grouped)
         graph_of_edge = np.searchsorted(np.asarray(ptr[1:]), ei[0], side='right') if ei.shape[1] else np.zeros(0, dtype=np.int64)
         order_ok = ei.shape[1] == 0 or bool(np.all(np.diff(graph_of_edge) >= 0))

@@ -207,7 +207,7 @@ class PretrainableGNN(nn.Module):
         mask-token write / target gather are one row-scatter and one row-gather kernel."""
         with torch.no_grad():
             h0 = self.input_encoders[domain_name](batch.x)
-        bounds = batch.ptr.tolist()
+        bounds = getattr(batch, '_ptr_host', None) or batch.ptr.tolist()      # gnnb200.loader batches carry a host mirror
         chosen = []
         for g in range(batch.num_graphs):
             lo, n = bounds[g], bounds[g + 1] - bounds[g]

@@ -1,0 +1,103 @@
+"""gnnb200.loader (device-resident datasets, index-gather batching, the balanced multi-domain sampler) on CPU: batches
+are identical tensor for tensor to `Batch.from_data_list` of the same picks (product Batch and the PyG shim's), and the
+sampler reproduces the reference's own `BalancedMultiDomainSampler` stream (container only for that part)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_batch
+from oracle.reference_loader import load_reference, reference_available
+
+import gnnb200  # noqa: F401
+from gnnb200 import loader, synthetic
+from gnnb200.data import Batch, Data
+
+
+def _graphs(domain, n, seed):
+    return [Data(**g) for g in synthetic.tu_like_graphs(domain, n, seed=seed)]
+
+
+def _same(a, b, names=('x', 'edge_index', 'batch', 'ptr', 'y', 'graph_properties')):
+    for k in names:
+        va, vb = getattr(a, k), getattr(b, k)
+        assert va.dtype == vb.dtype and torch.equal(va, vb), k
+    assert a.num_graphs == b.num_graphs
+
+
+@pytest.mark.parametrize('picks', [[0], [3, 3, 1], [11, 0, 5, 7, 2, 2, 9, 10], list(range(12))])
+def test_batch_of_equals_from_data_list(picks):
+    graphs = _graphs('ENZYMES', 12, seed=1)
+    graphs[5] = Data(x=graphs[5].x[:2], edge_index=torch.empty(2, 0, dtype=torch.long), y=graphs[5].y,
+                     graph_properties=graphs[5].graph_properties)                     # a graph without edges
+    res = loader.ResidentDomain(graphs)
+    got = res.batch_of(picks)
+    want = Batch.from_data_list([graphs[i] for i in picks])
+    _same(got, want)
+    # host mirrors the planners use instead of reading the structure back from the device
+    assert got._ptr_host == want.ptr.tolist()
+    assert np.array_equal(got._edge_index_host, want.edge_index.numpy())
+    # to_data_list() round trip (the reference's augmentation path, augmentations.py:91)
+    for g, orig in zip(got.to_data_list(), (graphs[i] for i in picks)):
+        for k in ('x', 'edge_index', 'y', 'graph_properties'):
+            assert torch.equal(getattr(g, k), getattr(orig, k)), k
+    # ... and against the oracle's PyG shim
+    _same(got, oracle_batch([{k: getattr(graphs[i], k) for k in graphs[i].keys()} for i in picks]))
+
+
+def test_segments_helper():
+    assert loader._segments(np.array([5, 0, 9]), np.array([2, 0, 3])).tolist() == [5, 6, 9, 10, 11]
+    assert loader._segments(np.array([4]), np.array([0])).size == 0
+
+
+def test_sampler_draws_and_sequential_batches():
+    graphs = {d: _graphs(d, 20, seed=i) for i, d in enumerate(['MUTAG', 'ENZYMES'])}
+    sets = {d: loader.GraphDataset(g, list(range(0, 20, 2))) for d, g in graphs.items()}
+    s = loader.BalancedMultiDomainSampler(sets, torch.Generator().manual_seed(3), batch_size=8)
+    assert len(s) == 10 // 4 and s.samples_per_domain == 4
+    g2 = torch.Generator().manual_seed(3)
+    for step in s:
+        assert list(step) == ['MUTAG', 'ENZYMES']
+        for d in step:
+            picks = torch.randint(0, 10, (4,), generator=g2).tolist()
+            _same(step[d], Batch.from_data_list([sets[d][i] for i in picks]))
+    val = loader.sequential_batches(sets['MUTAG'], batch_size=4)
+    assert [b.num_graphs for b in val] == [4, 4, 2]
+    _same(val[2], Batch.from_data_list([sets['MUTAG'][8], sets['MUTAG'][9]]))
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference not present')
+def test_sampler_equals_reference_sampler():
+    load_reference()
+    import src.data.pretrain_data_loaders as ref_loaders
+    from torch_geometric.data import Data as ShimData
+    domains = ['MUTAG', 'PROTEINS', 'NCI1', 'ENZYMES']
+    raw = {d: synthetic.tu_like_graphs(d, 30, seed=10 + i) for i, d in enumerate(domains)}
+    splits = {d: torch.randperm(30, generator=torch.Generator().manual_seed(i))[:21] for i, d in enumerate(domains)}
+    ref_sets = {d: ref_loaders.GraphDataset([ShimData(**g) for g in raw[d]], splits[d].numpy()) for d in domains}
+    my_sets = {d: loader.GraphDataset([Data(**g) for g in raw[d]], splits[d].numpy()) for d in domains}
+    a = ref_loaders.BalancedMultiDomainSampler(ref_sets, torch.Generator().manual_seed(42))
+    b = loader.BalancedMultiDomainSampler(my_sets, torch.Generator().manual_seed(42))
+    assert len(a) == len(b) and a.samples_per_domain == b.samples_per_domain == 8
+    steps = 0
+    for want, got in zip(a, b):
+        assert list(want) == list(got)
+        for d in domains:
+            _same(got[d], want[d])
+        steps += 1
+    assert steps == len(a) == 2
+
+
+def test_resident_batches_feed_the_host_planners_without_readback():
+    """A loader batch (host mirrors attached) gives the augmentation planner the same views as the collated batch."""
+    from gnnb200 import augment
+    graphs = _graphs('ENZYMES', 16, seed=4)
+    picks = [3, 3, 0, 15, 8, 9, 2, 11]
+    mirrored = loader.ResidentDomain(graphs).batch_of(picks)
+    plain = Batch.from_data_list([graphs[i] for i in picks])
+    assert getattr(plain, '_edge_index_host', None) is None
+    for seed in (0, 5):
+        a = augment.GraphAugmentor.create_two_views(mirrored, torch.Generator().manual_seed(seed))
+        b = augment.GraphAugmentor.create_two_views(plain, torch.Generator().manual_seed(seed))
+        for va, vb in zip(a[:2], b[:2]):
+            assert torch.equal(va.x, vb.x) and torch.equal(va.edge_index, vb.edge_index) and torch.equal(va.ptr, vb.ptr)
+        assert all(torch.equal(x, y) for x, y in zip(a[2] + a[3], b[2] + b[3]))
