@@ -74,7 +74,7 @@ class GINLayer(nn.Module):
     def forward(self, h: Tensor, edge_index: Tensor) -> Tensor:
         # 5 kernels per layer forward: gather(+self term) -> GEMM -> BN+ReLU -> GEMM(+residual h) -> BN+ReLU+dropout
         mlp = self.gin_conv.nn
-        if (self.fused and isinstance(edge_index, Tensor) and h.is_cuda and h.dim() == 2 and h.size(1) % 4 == 0
+        if (self.fused and isinstance(edge_index, Tensor) and ops.on_device(h) and h.dim() == 2 and h.size(1) % 4 == 0
                 and mlp[1].momentum is not None and self.batch_norm.momentum is not None):
             graph = graph_of(edge_index, h.size(0))
             p = DROPOUT_RATE if self.training else 0.0

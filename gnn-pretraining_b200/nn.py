@@ -71,9 +71,9 @@ class BatchNormAct(torch.nn.BatchNorm1d):
         """stats = (column sums, centred second moments) of x when a producer already computed them."""
         use_batch_stats = self.training or self.running_mean is None
         p = float(drop_p) if self.training else 0.0
-        fusable = (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and x.size(1) % 4 == 0
+        fusable = (x.dim() == 2 and x.dtype == torch.float32 and x.size(1) % 4 == 0
                    and self.affine and (self.momentum is not None or not use_batch_stats) and x.size(0) > 0)
-        if not x.is_cuda:
+        if not ops.on_device(x):
             raise L.Gnnb200Error('gnnb200 modules run on CUDA tensors only (no CPU fallback)')
         if not fusable:      # CUDA layouts outside the hot path (never hit by the reference's 256/512-wide layers)
             y = super().forward(x)

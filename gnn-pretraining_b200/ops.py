@@ -36,9 +36,15 @@ def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def on_device(t: Tensor) -> bool:
+    """True when `t` lives where the kernels run.  The single place the package asks that question, so that the
+    host-overhead profiler (scripts/host_profile.py) can run the Python layers with the kernels stubbed out."""
+    return t.is_cuda
+
+
 def _need_cuda(*tensors: Optional[Tensor]) -> None:
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is not None and not on_device(t):
             raise L.Gnnb200Error('gnnb200 ops run on CUDA tensors only (no CPU fallback)')
 
 
