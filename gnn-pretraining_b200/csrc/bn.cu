@@ -12,27 +12,18 @@
 // regenerated in the backward pass.  It is Bernoulli(1-p) with 1/(1-p) scaling like torch's, but not the
 // same bit stream as torch's CUDA generator (the reference's CPU and CUDA streams differ from each other too).
 #include "common.cuh"
+#include "ew_common.cuh"
 
 namespace gnnb200 {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-  uint32_t c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-
-// keep flags for the 4 consecutive elements starting at linear index 4*q
-__device__ __forceinline__ void keep4(uint64_t seed, uint64_t q, uint32_t thresh, bool (&k)[4]) {
-  const uint4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
-  k[0] = r.x < thresh; k[1] = r.y < thresh; k[2] = r.z < thresh; k[3] = r.w < thresh;
-}
+// elementwise_v2.cu (GNNB200_EW_V2=1): column-stationary variants; GNNB200_EUNSUPPORTED = shape not covered
+int bn_act_fwd_v2(const float* x, int64_t ldx, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, int relu, bool drop, uint64_t seed, uint32_t thresh, float scale, int64_t rows,
+                  int64_t cols, float* y, int64_t ldy, cudaStream_t stream);
+int bn_act_bwd_apply_v2(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* mean, const float* invstd,
+                        const float* gamma, const float* beta, const float* dgamma, const float* dbeta, int relu,
+                        int training, bool drop, uint64_t seed, uint32_t thresh, float scale, int64_t rows,
+                        int64_t rows_total, int64_t cols, float* dx, int64_t lddx, cudaStream_t stream);
 
 __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ m2, float n, float eps,
                                    float momentum, int cols, float* __restrict__ running_mean,
@@ -85,26 +76,6 @@ bn_act_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
 }
 
 constexpr int kBnRows = 256;
-
-// g1 for element (r, c..c+3) recomputed from the saved pre-BN activation
-template <bool DROP>
-__device__ __forceinline__ void bn_g1(const float4 g, const float4 v, const float4 mu, const float4 is, const float4 ga,
-                                      const float4 be, int relu, uint64_t seed, uint64_t q, uint32_t thresh, float scale,
-                                      float (&g1)[4], float (&xh)[4]) {
-  const float gv[4] = {g.x, g.y, g.z, g.w};
-  xh[0] = (v.x - mu.x) * is.x; xh[1] = (v.y - mu.y) * is.y; xh[2] = (v.z - mu.z) * is.z; xh[3] = (v.w - mu.w) * is.w;
-  const float gav[4] = {ga.x, ga.y, ga.z, ga.w};
-  const float bev[4] = {be.x, be.y, be.z, be.w};
-  bool k[4] = {true, true, true, true};
-  if (DROP) keep4(seed, q, thresh, k);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float t = gv[i];
-    if (DROP) t = k[i] ? t * scale : 0.f;
-    if (relu && !(xh[i] * gav[i] + bev[i] > 0.f)) t = 0.f;
-    g1[i] = t;
-  }
-}
 
 // Block = 32 column-quads (128 columns) x 8 row lanes over kBnRows rows; partial [chunks][2][cols].
 template <bool DROP>
@@ -253,6 +224,10 @@ extern "C" int gnnb200_bn_act_fwd_f32(const float* x, int64_t ldx, const float* 
   if (!bn_layout_ok(cols, ldx, ldy, x, y)) return GNNB200_EUNSUPPORTED;
   const uint32_t thresh = (uint32_t)((double)(1.f - drop_p) * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)(1.f - drop_p) * 4294967296.0);
   const float scale = 1.f / (1.f - drop_p);
+  if (ew_v2_enabled()) {
+    const int rc = bn_act_fwd_v2(x, ldx, mean, invstd, gamma, beta, relu, drop_p > 0.f, seed, thresh, scale, rows, cols, y, ldy, stream);
+    if (rc != GNNB200_EUNSUPPORTED) return rc;
+  }
   const int grid = ew_grid(rows * (cols / 4));
   if (drop_p > 0.f)
     bn_act_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, mean, invstd, gamma, beta, relu, seed, thresh, scale, rows, (int)cols, y, ldy);
@@ -299,6 +274,11 @@ extern "C" int gnnb200_bn_act_bwd_f32(const float* grad_y, int64_t ldg, const fl
   GNNB200_LAUNCH_CHECK();
   if (phase == 1) return GNNB200_OK;
 apply : {
+  if (ew_v2_enabled()) {
+    const int rc = bn_act_bwd_apply_v2(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, drop, seed,
+                                       thresh, scale, rows, rows_total, cols, grad_x, ldgx, stream);
+    if (rc != GNNB200_EUNSUPPORTED) return rc;
+  }
   const int grid = ew_grid(rows * (cols / 4));
   if (drop)
     bn_act_bwd_apply_kernel<true><<<grid, 256, 0, stream>>>(grad_y, ldg, x, ldx, mean, invstd, gamma, beta, dgamma, dbeta, relu, training, seed, thresh, scale, rows, rows_total, (int)cols, grad_x, ldgx);

@@ -2,6 +2,7 @@
 // autograd) and per-column statistics (BatchNorm1d batch statistics, reference
 // src/models/gnn.py:15,32,38; bias gradients of nn.Linear).  Two-stage, fixed order, no atomics.
 #include "common.cuh"
+#include "ew_common.cuh"
 
 namespace gnnb200 {
 
@@ -64,22 +65,6 @@ dot_finish_kernel(const float* __restrict__ partial, int count, float* __restric
 // first/second moment (shift = first value seen) so the second moment does not cancel, then the 4
 // row lanes and afterwards the row chunks are merged with Chan's parallel-variance formula.
 constexpr int kStatRows = 256;
-
-struct Moments {
-  float n, sum, m2;  // count, plain sum, centred second moment
-};
-
-__device__ __forceinline__ Moments merge(Moments a, Moments b) {
-  if (b.n == 0.f) return a;
-  if (a.n == 0.f) return b;
-  const float n = a.n + b.n;
-  const float d = b.sum / b.n - a.sum / a.n;
-  Moments r;
-  r.n = n;
-  r.sum = a.sum + b.sum;
-  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / n);
-  return r;
-}
 
 __global__ void __launch_bounds__(512)
 colstats_partial_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
@@ -152,6 +137,11 @@ int colstats_finish(const float* part, long long chunks, long long cols, float* 
 
 }  // namespace gnnb200
 
+namespace gnnb200 {
+// elementwise_v2.cu (GNNB200_EW_V2=1): 128-bit loads, 4 rows in flight per lane; same partial layout
+int colstats_partial_v2(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* part, cudaStream_t stream);
+}  // namespace gnnb200
+
 using namespace gnnb200;
 
 extern "C" int gnnb200_dot_f32(const float* a, const float* b, int64_t n, float* out, void* workspace,
@@ -192,10 +182,17 @@ extern "C" int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, i
   if (*workspace_bytes < ws.bytes()) return GNNB200_EWORKSPACE;
   if (cols == 0) return GNNB200_OK;
   if (rows > 0 && !x) return GNNB200_EINVAL;
-  dim3 grid((unsigned)((cols + 127) / 128), (unsigned)chunks);
-  dim3 block(128, 4);
-  colstats_partial_kernel<<<grid, block, 0, stream>>>(x, ldx, rows, (int)cols, part);
-  GNNB200_LAUNCH_CHECK();
+  int rc = GNNB200_EUNSUPPORTED;
+  if (ew_v2_enabled()) {
+    rc = colstats_partial_v2(x, ldx, rows, cols, part, stream);
+    if (rc != GNNB200_OK && rc != GNNB200_EUNSUPPORTED) return rc;
+  }
+  if (rc == GNNB200_EUNSUPPORTED) {
+    dim3 grid((unsigned)((cols + 127) / 128), (unsigned)chunks);
+    dim3 block(128, 4);
+    colstats_partial_kernel<<<grid, block, 0, stream>>>(x, ldx, rows, (int)cols, part);
+    GNNB200_LAUNCH_CHECK();
+  }
   colstats_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)chunks, (int)cols, sum, m2);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
