@@ -451,26 +451,11 @@ S5_TASKS = S4_TASKS + ['domain_adv']
 TU_DOMAINS = ['MUTAG', 'PROTEINS', 'NCI1', 'ENZYMES']
 
 
-def run_c4(args):
-    """Every rank trains the s5 multi-task step on its own graphs: 128 per step (32 per TU-shaped domain) drawn by the
-    balanced multi-domain sampler from that rank's device-resident dataset (256 graphs per domain, seed 42 + rank).
-    One step = gnnb200.pretrain.train_step, i.e. the reference's run_training iteration (src/pretrain/pretrain.py:112-184):
-    task losses -> loss balancer -> gradient surgery over the five main tasks -> domain-adversarial backward through the
-    GRL on top -> [one flat NCCL all-reduce of the gradients, mean] -> clip -> task-specific AdamW -> schedulers -> metrics.
-    BatchNorm statistics stay per replica (DDP semantics).  Weak scaling: value = global steps/s (the same on every N),
-    graphs/s = 128 * N * steps/s.  Device leg: the same resident batches every step; e2e leg: a fresh draw per step
-    (upload of the packed gather indices) and the metrics dict read back."""
+def build_c4_step(dev, rank, world):
+    """(step(batches) -> metrics, sampler) of the C4 workload on `dev` for this rank (see run_c4)."""
     import random
-    import torch.distributed as dist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     import gnnb200  # noqa: F401
-    from gnnb200 import data as data_mod, loader, models, ops, partition, pretrain, synthetic, tasks as task_mod
+    from gnnb200 import data as data_mod, loader, models, partition, pretrain, synthetic, tasks as task_mod
     from gnnb200.gradient_surgery import GradientSurgery
     torch.manual_seed(0)
     pm = models.PretrainableGNN(dev, TU_DOMAINS, S5_TASKS)
@@ -495,6 +480,30 @@ def run_c4(args):
     def step(batches):
         return pretrain.train_step(pm, tasks, opt, batches, gen, grl, temp, balancer, surgery, TU_DOMAINS,
                                    allreduce=mean_allreduce if world > 1 else None)
+    step.model, step.schedulers = pm, (grl, temp, balancer)
+    return step, sampler
+
+
+def run_c4(args):
+    """Every rank trains the s5 multi-task step on its own graphs: 128 per step (32 per TU-shaped domain) drawn by the
+    balanced multi-domain sampler from that rank's device-resident dataset (256 graphs per domain, seed 42 + rank).
+    One step = gnnb200.pretrain.train_step, i.e. the reference's run_training iteration (src/pretrain/pretrain.py:112-184):
+    task losses -> loss balancer -> gradient surgery over the five main tasks -> domain-adversarial backward through the
+    GRL on top -> [one flat NCCL all-reduce of the gradients, mean] -> clip -> task-specific AdamW -> schedulers -> metrics.
+    BatchNorm statistics stay per replica (DDP semantics).  Weak scaling: value = global steps/s (the same on every N),
+    graphs/s = 128 * N * steps/s.  Device leg: the same resident batches every step; e2e leg: a fresh draw per step
+    (upload of the packed gather indices) and the metrics dict read back."""
+    import random
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+    from gnnb200 import ops
+    step, sampler = build_c4_step(dev, rank, world)
 
     def barrier():
         if world > 1:
