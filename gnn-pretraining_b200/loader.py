@@ -173,3 +173,59 @@ def sequential_batches(dataset: GraphDataset, batch_size: int = BATCH_SIZE, devi
     consecutive slices of the split, cut from the resident copy."""
     resident = ResidentDomain([dataset[i] for i in range(len(dataset))], device)
     return [resident.batch_of(range(lo, min(lo + batch_size, len(dataset)))) for lo in range(0, len(dataset), batch_size)]
+
+
+# ---- fine-tuning loaders (reference src/data/finetune_data_loaders.py) -----------------------------------------------
+# The reference wraps a single graph in a Dataset that returns one (data, node, label) / (data, edge, label) tuple per
+# ITEM and rebuilds every batch with `torch.tensor([item[..] for item in batch])` — one Python object and one scalar
+# read per node or edge.  Its DataLoaders never shuffle (shuffle=False is the default; the generator is unused), so a
+# batch is simply a consecutive slice of the split: the classes below keep the graph and the split resident on the device
+# and yield those slices (same tuple layout, dtypes and order).
+
+
+class NodeBatches:
+    """create_node_classification_loader (:81-95): yields (data, node_indices [b] int64, labels [b] int64)."""
+
+    def __init__(self, data, indices, batch_size: int, device: Optional[torch.device] = None) -> None:
+        self.data = data.to(device) if device is not None else data
+        dev = self.data.x.device
+        self.indices = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(dev)
+        self.labels = self.data.y[self.indices].to(torch.long)
+        self.batch_size = len(self.indices) if batch_size == -1 else int(batch_size)
+        self.dataset = self
+
+    def __len__(self) -> int:
+        return (len(self.indices) + self.batch_size - 1) // self.batch_size if len(self.indices) else 0
+
+    def __iter__(self):
+        for lo in range(0, len(self.indices), self.batch_size):
+            yield self.data, self.indices[lo:lo + self.batch_size], self.labels[lo:lo + self.batch_size]
+
+
+class LinkBatches:
+    """create_link_prediction_loader (:98-107) over LinkPredictionDataset (:27-52): training batches are positive edges
+    with label 1 (negatives are mined per step, finetune.py:186-196); validation / test batches are positives followed by
+    the split's fixed negatives.  `.dataset.train_edges` is what the training loop reads (finetune.py:304, :350)."""
+
+    def __init__(self, data, split_edges: Dict[str, Tensor], split: str, batch_size: int,
+                 device: Optional[torch.device] = None) -> None:
+        self.data = data.to(device) if device is not None else data
+        dev = self.data.x.device
+        self.split = split
+        self.train_edges = split_edges['train_pos'].to(dev)
+        if split == 'train':
+            self.edges = self.train_edges
+            self.labels = torch.ones(self.edges.size(1), device=dev)
+        else:
+            pos, neg = split_edges[f'{split}_pos'].to(dev), split_edges[f'{split}_neg'].to(dev)
+            self.edges = torch.cat([pos, neg], dim=1)
+            self.labels = torch.cat([torch.ones(pos.size(1), device=dev), torch.zeros(neg.size(1), device=dev)])
+        self.batch_size = int(batch_size)
+        self.dataset = self
+
+    def __len__(self) -> int:
+        return (self.edges.size(1) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for lo in range(0, self.edges.size(1), self.batch_size):
+            yield self.data, self.edges[:, lo:lo + self.batch_size], self.labels[lo:lo + self.batch_size]

@@ -101,3 +101,38 @@ def test_resident_batches_feed_the_host_planners_without_readback():
         for va, vb in zip(a[:2], b[:2]):
             assert torch.equal(va.x, vb.x) and torch.equal(va.edge_index, vb.edge_index) and torch.equal(va.ptr, vb.ptr)
         assert all(torch.equal(x, y) for x, y in zip(a[2] + a[3], b[2] + b[3]))
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference not present')
+def test_finetune_loaders_equal_reference_loaders():
+    """NodeBatches / LinkBatches against the reference's item-wise datasets + collate functions driven by a real
+    torch DataLoader (src/data/finetune_data_loaders.py:14-107)."""
+    load_reference()
+    import src.data.finetune_data_loaders as ref
+    from torch_geometric.data import Data as ShimData
+    d = synthetic.planetoid_like(200, 400, 16, seed=2)
+    y = torch.randint(0, 7, (200,), generator=torch.Generator().manual_seed(0))
+    split = torch.randperm(200, generator=torch.Generator().manual_seed(1))[:70]
+    gen = torch.Generator().manual_seed(9)
+    for bs in (-1, 32):
+        ref_data = ShimData(x=d['x'], edge_index=d['edge_index'], y=y)
+        ds = ref.NodeDataset(ref_data, split.numpy())
+        want = list(torch.utils.data.DataLoader(ds, batch_size=len(ds) if bs == -1 else bs, generator=gen,
+                                                collate_fn=ref._collate_node_batch))
+        got = list(loader.NodeBatches(Data(x=d['x'], edge_index=d['edge_index'], y=y), split.numpy(), bs))
+        assert len(want) == len(got) == len(loader.NodeBatches(Data(x=d['x'], edge_index=d['edge_index'], y=y), split.numpy(), bs))
+        for (wd, wi, wl), (gd, gi, gl) in zip(want, got):
+            assert torch.equal(wd.x, gd.x) and torch.equal(wd.edge_index, gd.edge_index)
+            assert wi.dtype == gi.dtype and torch.equal(wi, gi) and wl.dtype == gl.dtype and torch.equal(wl, gl)
+    e = d['edge_index']
+    splits = {'train_pos': e[:, :300], 'val_pos': e[:, 300:350], 'val_neg': e[:, 350:400].flip(0),
+              'test_pos': e[:, 400:470], 'test_neg': e[:, 470:540].flip(0)}
+    for name in ('train', 'val', 'test'):
+        ref_data = ShimData(x=d['x'], edge_index=d['edge_index'])
+        ds = ref.LinkPredictionDataset(ref_data, splits, name)
+        want = list(torch.utils.data.DataLoader(ds, batch_size=64, generator=gen, collate_fn=ref._collate_link_batch))
+        mine = loader.LinkBatches(Data(x=d['x'], edge_index=d['edge_index']), splits, name, 64)
+        got = list(mine)
+        assert len(want) == len(got) == len(mine) and torch.equal(mine.dataset.train_edges, ds.train_edges)
+        for (wd, we, wl), (gd, ge, gl) in zip(want, got):
+            assert we.dtype == ge.dtype and torch.equal(we, ge) and wl.dtype == gl.dtype and torch.equal(wl, gl)
