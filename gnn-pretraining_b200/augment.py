@@ -137,4 +137,11 @@ class GraphAugmentor:
                 return []
             flat = torch.from_numpy(np.concatenate(masks)).to(dev)
             return list(torch.split(flat, [m.size for m in masks]))
-        return v1, v2, to_device(masks_a), to_device(masks_b)
+        dev_a, dev_b = to_device(masks_a), to_device(masks_b)
+        # rows of each view that survive in both (what NodeContrastiveTask gathers, reference tasks.py:153-164), computed
+        # here from the host masks: the device masks would cost one nonzero() = one device sync per graph and view
+        for view, host_masks, dev_masks in ((v1, masks_a, dev_a), (v2, masks_b, dev_b)):
+            starts = view._ptr_host
+            rows = [np.flatnonzero(m) + starts[g] for g, m in enumerate(host_masks)]
+            view._common_rows_host = (dev_masks, np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64))
+        return v1, v2, dev_a, dev_b

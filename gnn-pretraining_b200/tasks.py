@@ -168,6 +168,9 @@ class NodeContrastiveTask(BasePretrainTask):
 
     @staticmethod
     def _common_rows(view, masks) -> Tensor:
+        planned = getattr(view, '_common_rows_host', None)
+        if planned is not None and planned[0] is masks:      # views made by gnnb200.augment carry the answer (host side)
+            return torch.from_numpy(planned[1])
         starts = getattr(view, '_ptr_host', None) or view.ptr.tolist()
         rows = [torch.nonzero(m, as_tuple=False).view(-1) + starts[g] for g, m in enumerate(masks)]
         return torch.cat(rows) if rows else torch.empty(0, dtype=torch.long, device=view.x.device)

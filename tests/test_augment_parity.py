@@ -59,3 +59,19 @@ def test_single_large_graph_cora_shape():
     assert torch.equal(o1.x, p1.x) and torch.equal(o1.edge_index, p1.edge_index)
     assert torch.equal(o2.x, p2.x) and torch.equal(o2.edge_index, p2.edge_index)
     assert torch.equal(om1[0], pm1[0]) and torch.equal(om2[0], pm2[0])
+
+
+def test_common_rows_planned_on_the_host_equal_the_mask_path():
+    """NodeContrastiveTask._common_rows: the host-planned row indices attached to the views equal what the per-graph
+    nonzero() over the device masks gives (reference tasks.py:153-164), without one device sync per graph."""
+    from gnnb200.tasks import NodeContrastiveTask
+    graphs = synthetic.tu_like_graphs('ENZYMES', 12, seed=6)
+    for seed in (0, 3):
+        v1, v2, m1, m2 = augment.GraphAugmentor.create_two_views(_product_batch(graphs), torch.Generator().manual_seed(seed))
+        for view, masks in ((v1, m1), (v2, m2)):
+            planned = NodeContrastiveTask._common_rows(view, masks)
+            assert view._common_rows_host[0] is masks
+            via_masks = NodeContrastiveTask._common_rows(view, list(masks))        # a different list object: mask path
+            assert planned.dtype == via_masks.dtype == torch.long and torch.equal(planned, via_masks)
+        # both views keep the same nodes in common, graph by graph
+        assert NodeContrastiveTask._common_rows(v1, m1).numel() == NodeContrastiveTask._common_rows(v2, m2).numel()
