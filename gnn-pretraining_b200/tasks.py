@@ -6,6 +6,7 @@ loss normalisation (sum / integer count, divided once) follows the reference."""
 import math
 from typing import Dict, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 from torch import Tensor
@@ -139,14 +140,31 @@ class NodeFeatureMaskingTask(BasePretrainTask):
 class LinkPredictionTask(BasePretrainTask):
     """reference tasks.py:97-127."""
 
+    @staticmethod
+    def _negatives(batch, pos: Tensor) -> Tensor:
+        """tasks.py:107-111: batched_negative_sampling(to_undirected(edge_index), batch, E).  Batches cut by
+        gnnb200.loader carry the structure on the host: symmetrise + coalesce + sampling then run there and only the
+        result is uploaded (no coalesce kernels, no count read-back, no edge-list download)."""
+        ei_host, ptr_host = getattr(batch, '_edge_index_host', None), getattr(batch, '_ptr_host', None)
+        if ei_host is None or ptr_host is None:
+            return batched_negative_sampling(edge_index=to_undirected(pos), batch=batch.batch, num_neg_samples=pos.size(1))
+        if pos.size(1) == 0:
+            return pos.new_empty((2, 0))
+        from .utils import batched_negative_sampling_host, to_undirected_host
+        # like the device path, the node count of coalesce() is max index + 1 and graphs are read off `batch`
+        und = to_undirected_host(ei_host, int(ei_host.max()) + 1)
+        neg = batched_negative_sampling_host(und, np.diff(np.asarray(ptr_host, dtype=np.int64)), pos.size(1))
+        if neg is None:
+            return pos.new_empty((2, 0))
+        return torch.from_numpy(neg).to(pos.device)
+
     def compute_loss(self, domain_batches, generator):
         dev = self.model.device
         total, count, per_domain = self._start()
         decoder = self.model.get_head('link_pred')
         for name, batch in domain_batches.items():
             pos = batch.edge_index
-            neg = batched_negative_sampling(edge_index=to_undirected(pos), batch=batch.batch,
-                                            num_neg_samples=pos.size(1))
+            neg = self._negatives(batch, pos)
             edges = torch.cat([pos, neg], dim=1)
             labels = torch.cat([torch.ones(pos.size(1), device=dev), torch.zeros(neg.size(1), device=dev)])
             probs = decoder(self.model(batch, name), edges)

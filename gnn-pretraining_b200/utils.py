@@ -104,13 +104,32 @@ def batched_negative_sampling(edge_index: Tensor, batch: Tensor, num_neg_samples
     upstream.  One device->host transfer (edge list and graph ids together), one upload of the result."""
     if method != 'sparse' or force_undirected:
         raise NotImplementedError('only the branch used by the reference is provided')
-    device = edge_index.device
     e_total = edge_index.size(1)
     if e_total == 0:
         return edge_index.new_empty((2, 0))
     host = torch.cat([edge_index.reshape(-1), batch]).cpu().numpy()
     ei, graph_of_node = host[:2 * e_total].reshape(2, e_total), host[2 * e_total:]
-    sizes = np.bincount(graph_of_node)                                           # nodes per graph
+    found = batched_negative_sampling_host(ei, np.bincount(graph_of_node), num_neg_samples)
+    if found is None:
+        return edge_index.new_empty((2, 0))
+    return torch.from_numpy(found).to(edge_index.device)
+
+
+def to_undirected_host(edge_index: np.ndarray, num_nodes: int) -> np.ndarray:
+    """`to_undirected` (App. A.4) on a host copy of the edge list: symmetrise, sort by row*N+col, drop duplicates."""
+    key = np.unique(np.concatenate([edge_index[0] * num_nodes + edge_index[1], edge_index[1] * num_nodes + edge_index[0]]))
+    return np.stack([key // num_nodes, key % num_nodes])
+
+
+def batched_negative_sampling_host(ei: np.ndarray, sizes: np.ndarray, num_neg_samples: Optional[int] = None
+                                   ) -> Optional[np.ndarray]:
+    """The host core of `batched_negative_sampling`: `ei` [2, E] int64 grouped by graph, `sizes` = nodes per graph.
+    Returns [2, K] int64 (None when no negative exists).  Callers that already hold the structure on the host
+    (gnnb200.loader batches) use it directly and skip the device round trip."""
+    e_total = ei.shape[1]
+    if e_total == 0:
+        return None
+    graph_of_node = np.repeat(np.arange(sizes.size), sizes)
     starts = np.cumsum(sizes) - sizes
     graph_of_edge = graph_of_node[ei[0]]
     per_graph = np.bincount(graph_of_edge)                # like upstream: graphs after the last one with an edge are skipped
@@ -162,5 +181,5 @@ def batched_negative_sampling(edge_index: Tensor, batch: Tensor, num_neg_samples
         pieces[g] = (negative_sampling(local_edges, int(n[g]), want) + int(starts[g])).numpy()
     found = [p for p in pieces if p is not None]
     if not found:
-        return edge_index.new_empty((2, 0))
-    return torch.from_numpy(np.concatenate(found, axis=1)).to(device)
+        return None
+    return np.concatenate(found, axis=1)

@@ -3,6 +3,7 @@
 App. A.5): bit-identical negatives in the same order and the same position of Python's `random` stream afterwards."""
 import random
 
+import numpy as np
 import pytest
 import torch
 
@@ -74,3 +75,23 @@ def test_ungrouped_edges_are_refused():
                               Data(x=torch.randn(3, 2), edge_index=torch.tensor([[0], [2]]))])
     with pytest.raises(ValueError):
         utils.batched_negative_sampling(b.edge_index.flip(1), b.batch, 2)
+
+
+@pytest.mark.parametrize('domain', ['ENZYMES', 'MUTAG'])
+def test_link_prediction_negatives_from_the_host_mirror(domain):
+    """LinkPredictionTask._negatives on a gnnb200.loader batch (structure mirrored on the host: symmetrise + coalesce +
+    sampling never touch the device) equals the oracle's to_undirected + batched_negative_sampling on the same batch."""
+    from gnnb200 import loader
+    from gnnb200.tasks import LinkPredictionTask
+    graphs = [Data(**g) for g in synthetic.tu_like_graphs(domain, 20, seed=3)]
+    graphs[7] = Data(x=graphs[7].x, edge_index=torch.empty(2, 0, dtype=torch.long), y=graphs[7].y,
+                     graph_properties=graphs[7].graph_properties)
+    picks = [4, 7, 7, 0, 19, 12, 4, 3]
+    b = loader.ResidentDomain(graphs).batch_of(picks)
+    random.seed(2)
+    got = LinkPredictionTask._negatives(b, b.edge_index)
+    random.seed(2)
+    want = pyg_utils.batched_negative_sampling(pyg_utils.to_undirected(b.edge_index), b.batch, b.edge_index.size(1))
+    assert got.dtype == torch.long and torch.equal(got, want)
+    assert np.array_equal(utils.to_undirected_host(b._edge_index_host, int(b.edge_index.max()) + 1),
+                          pyg_utils.to_undirected(b.edge_index).numpy())
