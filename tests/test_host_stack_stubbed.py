@@ -162,3 +162,13 @@ def test_partitioned_step_host_logic_over_gloo(tmp_path, halo, world):
         port = s.getsockname()[1]
     mp.spawn(_partition_worker, args=(world, port, halo, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+def test_bench_secondary_workloads_run_through_the_host_stack(stubbed):
+    """bench.py's C1 / C2 / C3 steps (Cora-shaped backbone, ENZYMES fine-tune step, s4 multi-task step on Cora / CiteSeer /
+    ENZYMES shaped domains incl. the `random.sample` negative-sampling branch and gradient surgery) with stubbed kernels."""
+    bench = _bench_module()
+    out = bench.small_graph_steps('gnnb200', torch.device('cpu'), steps=4, warmup=2)
+    assert out['c2_shape']['graphs'] == 128 and out['c3_shape']['tasks'] == bench.S4_TASKS
+    assert all(out[k] > 0 for k in ('c1_edges_per_s', 'c2_finetune_steps_per_s', 'c3_s4_pretrain_steps_per_s'))
+    assert stubbed['gnnb200_pcgrad_f32'] >= 2 and stubbed['gnnb200_ntxent_fwd_f32'] + stubbed.get('gnnb200_ntxent_sim_fwd_f32', 0) > 0
