@@ -1,15 +1,17 @@
 // Column-stationary variants of the BatchNorm(+ReLU+dropout) apply kernels and a vectorised column-statistics
 // kernel (selected by GNNB200_EW_V2=1, see ew_common.cuh).
 //
-// Why.  The launch list of the C5 step (profiles/r01_summary.md, r01-e) puts the first versions at
-//   bn_act_bwd_apply 72 %, bn_act_fwd 80 %, colstats_partial 53 % of the HBM roofline (bn_act_bwd_reduce: 87 %).
-// The two apply kernels walk the matrix as one flat grid-stride loop: every element pays a 64-bit division to find its
-// row, and re-loads six per-column parameter vectors (mean, invstd, gamma, beta, dgamma, dbeta) through L1 — three
-// times more load instructions than the two streams that actually come from HBM.  The statistics kernel reads 4 bytes
-// per lane with one row in flight.  The reduce kernel, which is column-stationary, does not have those problems —
-// so every kernel here takes its shape: a block owns 128 columns (32 lanes x float4) of a 256-row chunk, its 8 warps
-// interleave the rows, the per-column parameters live in registers for the whole chunk, and four rows' 128-bit loads
-// are issued before the first one is consumed.
+// Why.  Per-launch times of the C5 step at quarter scale (profiles/r01e_launches_scale0.25_tf32.csv; bytes / time against
+// the measured 6.55 TB/s copy peak):
+//   bn_act_fwd<no dropout, C=512> 0.99   bn_act_fwd<dropout, C=256> 0.62   colstats_partial 0.79-0.84 (+ 0.09 ms finish)
+//   bn_act_bwd_reduce 0.93 / 0.77        bn_act_bwd_apply<C=512> 0.69      bn_act_bwd_apply<dropout, C=256> 0.80
+// The two apply kernels walk the matrix as one flat grid-stride loop: every 4 elements pay a 64-bit division to find
+// their row and re-load the per-column parameter vectors (4 forward, 6 backward) through L1 — more load instructions
+// for parameters than for the streams that come from HBM; with dropout the Philox rounds on top make the forward kernel
+// issue-bound.  The statistics kernel reads 4 bytes per lane with one row in flight.  The reduce kernel, which is
+// column-stationary, has neither problem — so every kernel here takes its shape: a block owns 128 columns (32 lanes x
+// float4) of a 256-row chunk, its 8 warps interleave the rows, the per-column parameters live in registers for the
+// whole chunk, and several rows' 128-bit loads are issued before the first one is consumed.
 //
 // Same arithmetic expressions and the same Philox counter (row * cols/4 + column quad) as the first versions, so the
 // forward output, the regenerated dropout mask and dx are bit-identical to them; the statistics differ from the first
