@@ -139,7 +139,8 @@ int colstats_finish(const float* part, long long chunks, long long cols, float* 
 
 namespace gnnb200 {
 // elementwise_v2.cu (GNNB200_EW_V2=1): 128-bit loads, 4 rows in flight per lane; same partial layout
-int colstats_partial_v2(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* part, cudaStream_t stream);
+int colstats_partial_v2(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* part, int64_t* chunks_out,
+                        cudaStream_t stream);
 }  // namespace gnnb200
 
 using namespace gnnb200;
@@ -183,17 +184,19 @@ extern "C" int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, i
   if (cols == 0) return GNNB200_OK;
   if (rows > 0 && !x) return GNNB200_EINVAL;
   int rc = GNNB200_EUNSUPPORTED;
+  int64_t written = chunks;                    // chunks of `part` the partial kernel fills
   if (ew_v2_enabled()) {
-    rc = colstats_partial_v2(x, ldx, rows, cols, part, stream);
+    rc = colstats_partial_v2(x, ldx, rows, cols, part, &written, stream);
     if (rc != GNNB200_OK && rc != GNNB200_EUNSUPPORTED) return rc;
   }
   if (rc == GNNB200_EUNSUPPORTED) {
+    written = chunks;
     dim3 grid((unsigned)((cols + 127) / 128), (unsigned)chunks);
     dim3 block(128, 4);
     colstats_partial_kernel<<<grid, block, 0, stream>>>(x, ldx, rows, (int)cols, part);
     GNNB200_LAUNCH_CHECK();
   }
-  colstats_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)chunks, (int)cols, sum, m2);
+  colstats_finish_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 32), 0, stream>>>(part, (int)written, (int)cols, sum, m2);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
