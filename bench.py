@@ -8,7 +8,8 @@ InputEncoder + 5-layer GIN backbone in TRAIN mode (BatchNorm batch statistics, d
 loss = h.sum(), backward, AdamW step.  One step = CSR+CSC build from edge_index, forward,
 backward, optimizer.  metric = aggregated edges/sec = E * L * 2 (fwd + bwd sweeps) / step time.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S] [--locality P]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S] [--locality P] [--halo dense|sparse|auto]
+  python bench.py --workload c4 ...      BASELINE configs[3]: data-parallel s5 pre-training step (steps/s, weak scaling)
 
 N > 1 (launched by torch.distributed.run): the same graph node-partitioned into N contiguous
 destination ranges with an NCCL all-gather of the layer input per layer ("strong" scaling).
