@@ -48,7 +48,14 @@ SIGNATURES = {
     'gnnb200_ntxent_sim_fwd_f32': [P, I64, I64, c_float, P, P, P, P],
     'gnnb200_ntxent_sim_bwd_f32': [P, I64, I64, c_float, P, P, P],
     'gnnb200_pcgrad_f32': [P, P, I64, I64, P, I64, P, P, P, P, P, P, P],
+    'gnnb200_aggregate_peer_f32': [P, c_int, I64, P, P, I64, I64, P, I64, P, P, I64, P],
+    'gnnb200_peer_publish_f32': [P, I64, I64, I64, P, I64, P],
+    'gnnb200_peer_alloc': [c_size_t, POINTER(c_void_p), P],
+    'gnnb200_peer_open': [P, POINTER(c_void_p)],
+    'gnnb200_peer_close': [P],
+    'gnnb200_peer_free': [P],
 }
+PEER_SHIFT, MAX_PEERS, PEER_HANDLE_BYTES = 28, 16, 64
 
 _lib = None
 

@@ -79,6 +79,8 @@ KERNELS_PER_CALL = {
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
     'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,
+    'gnnb200_aggregate_peer_f32': 1, 'gnnb200_peer_publish_f32': 0, 'gnnb200_peer_alloc': 0, 'gnnb200_peer_open': 0,
+    'gnnb200_peer_close': 0, 'gnnb200_peer_free': 0,
 }
 _calls = {}
 AGG_TIMER = None      # bench.py sets this to a list to collect (start, stop) CUDA events per aggregation launch
@@ -283,6 +285,29 @@ def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Op
         _ptr(x), _ld(x), _ptr(rowptr), _ptr(col), n_rows, x.size(1), mode,
         _ptr(self_x), _ld(self_x) if self_x is not None else 0, _ptr(eps), _ptr(dinv),
         _ptr(out), _ld(out), _stream(x)), 'aggregate')
+    if timer is not None:
+        ev[1].record()
+        timer.append(ev)
+    return out
+
+
+def aggregate_peer(table: Tensor, ld: int, rowptr: Tensor, col: Tensor, feat: int, self_x: Optional[Tensor],
+                   eps: Optional[Tensor]) -> Tensor:
+    """Aggregation whose neighbour rows live in peer-mapped buffers of several GPUs (gnnb200_aggregate_peer_f32):
+    `table` int64 [P] on this device = base pointers of the published [rows, ld] fp32 buffers, `col` int32 with the
+    owner slot in bits 31..28.  SUM + optional (1+eps) self term; no autograd (see partition._PartitionedGINAggregate)."""
+    _need_cuda(table, rowptr, col, self_x, eps)
+    n_rows = rowptr.numel() - 1
+    out = torch.empty(n_rows, feat, dtype=torch.float32, device=table.device)
+    if self_x is not None:
+        self_x = _rowmajor(self_x)
+    timer = AGG_TIMER
+    if timer is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    L.check(_invoke('gnnb200_aggregate_peer_f32', _ptr(table), table.numel(), ld, _ptr(rowptr), _ptr(col), n_rows, feat,
+                    _ptr(self_x), _ld(self_x) if self_x is not None else 0, _ptr(eps), _ptr(out), _ld(out),
+                    _stream(table)), 'aggregate_peer')
     if timer is not None:
         ev[1].record()
         timer.append(ev)

@@ -42,10 +42,18 @@ DEFAULT_HALO_CHUNKS = 1
 #              [n_local + halo, F] that the local CSR indexes.  Same per-row edge order => same bits as 'dense'.
 #   'auto'   : 'sparse' iff the largest needed fraction of remote rows over all ranks is below
 #              SPARSE_HALO_MAX_FRACTION (one small all-reduce per graph, so every rank takes the same branch).
+#   'peer'   : no exchange step at all: every rank publishes its rows in a peer-mapped buffer (CUDA IPC over NVLink,
+#              PeerRows) and the gather kernel reads neighbour rows straight from the owning GPU
+#              (gnnb200_aggregate_peer_f32) — transfer and sums overlap inside ONE kernel, nothing is packed, staged
+#              or all-gathered; per pass one local copy of the shard and one barrier.  A remote row crosses NVLink once
+#              per referencing edge, so this is for graphs with locality; same per-row edge order => same bits.
 # 'sparse'/'auto' are covered by the gloo world-2 tests (index plan, exchange, algebra) but were written after the
 # round's GPU budget was spent: unmeasured on NCCL, hence opt-in (GNNB200_HALO or the `halo=` argument).
+# 'peer' was written at the same time; its kernel and column encoding are tested on one GPU against the
+# single-device kernel (virtual ranks = slices of one buffer), the IPC leg needs 2 GPUs and is equally unmeasured.
 DEFAULT_HALO = 'dense'
 SPARSE_HALO_MAX_FRACTION = 0.5
+HALO_MODES = ('dense', 'sparse', 'auto', 'peer')
 
 
 def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
@@ -103,6 +111,78 @@ def remote_fraction_needed(other: Tensor, lo: int, hi: int, num_nodes: int, grou
     return float(t)
 
 
+def encode_peer_columns(other: Tensor, per: int) -> Tensor:
+    """Global row ids -> (owner slot << 28) | row inside the owner's published buffer (int64 holding the int32 code
+    that gnnb200_aggregate_peer_f32 decodes).  Needs per <= 2^28 rows per rank and <= 8 ranks (code < 2^31)."""
+    owner = torch.div(other, per, rounding_mode='floor')
+    return (owner << L.PEER_SHIFT) | (other - owner * per)
+
+
+class PeerRows:
+    """This rank's two published row buffers ([rows, feat] fp32 each, allocated by gnnb200_peer_alloc) and the other
+    ranks' buffers mapped into this device's address space (CUDA IPC handles exchanged once over the process group).
+    `publish(x_local)` copies the shard into the next buffer, orders every rank behind it (one 4-byte all-reduce on
+    the stream = the barrier) and returns the device table of the P base pointers the gather kernel indexes.
+    Two buffers + one barrier per pass are enough: a rank can only overwrite buffer b two passes later, i.e. after a
+    barrier that every rank entered behind its own read of b."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, rows: int, feat: int, rank: int, world: int, group, device) -> 'PeerRows':
+        key = (id(group), rows, feat, rank, world, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(rows, feat, rank, world, group, device)
+        return cls._cache[key]
+
+    def __init__(self, rows: int, feat: int, rank: int, world: int, group, device):
+        import ctypes
+        if world > 8 or rows > (1 << L.PEER_SHIFT):
+            raise L.Gnnb200Error('peer halo: at most 8 ranks and 2^28 rows per rank')
+        self.rows, self.feat, self.rank, self.world, self.group = rows, feat, rank, world, group
+        self.turn = 0
+        self._mine, self._mapped, handles = [], [], []
+        for _ in range(2):
+            ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * L.PEER_HANDLE_BYTES)()
+            L.check(ops._invoke('gnnb200_peer_alloc', rows * feat * 4, ctypes.byref(ptr), handle), 'peer_alloc')
+            self._mine.append(ptr.value or 0)
+            handles.append(bytes(handle))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles, group=group)
+        tables = []
+        for b in range(2):
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(self._mine[b])
+                    continue
+                ptr = ctypes.c_void_p()
+                raw = (ctypes.c_ubyte * L.PEER_HANDLE_BYTES).from_buffer_copy(everyone[r][b])
+                L.check(ops._invoke('gnnb200_peer_open', raw, ctypes.byref(ptr)), f'peer_open (rank {r})')
+                self._mapped.append(ptr.value or 0)
+                ptrs.append(ptr.value or 0)
+            tables.append(ptrs)
+        self.tables = torch.tensor(tables, dtype=torch.int64).to(device)          # [2, P] base pointers
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def publish(self, x_local: Tensor) -> Tensor:
+        b = self.turn & 1
+        self.turn += 1
+        x_local = ops._rowmajor(x_local)
+        L.check(ops._invoke('gnnb200_peer_publish_f32', x_local.data_ptr(), ops._ld(x_local), x_local.size(0), self.feat,
+                            self._mine[b], self.feat, ops._stream(x_local)), 'peer_publish')
+        dist.all_reduce(self._flag, group=self.group)          # every rank's copy precedes every rank's gather
+        return self.tables[b]
+
+    def close(self) -> None:
+        for p in self._mapped:
+            ops._invoke('gnnb200_peer_close', p)
+        for p in self._mine:
+            ops._invoke('gnnb200_peer_free', p)
+        self._mapped, self._mine = [], []
+        PeerRows._cache = {k: v for k, v in PeerRows._cache.items() if v is not self}
+
+
 class PartitionedGraph:
     """This rank's slice of the graph.  Passed wherever the backbone expects ``edge_index``; GINConv
     recognises it and takes the partitioned aggregation.
@@ -121,8 +201,8 @@ class PartitionedGraph:
             chunks = int(os.environ.get('GNNB200_HALO_CHUNKS', DEFAULT_HALO_CHUNKS))
         if halo is None:
             halo = os.environ.get('GNNB200_HALO', DEFAULT_HALO)
-        if halo not in ('dense', 'sparse', 'auto'):
-            raise ValueError(f'halo must be dense, sparse or auto, not {halo!r}')
+        if halo not in HALO_MODES:
+            raise ValueError(f'halo must be one of {HALO_MODES}, not {halo!r}')
         self.num_nodes, self.rank, self.world, self.group = int(num_nodes), rank, world, group
         self.lo, self.hi, self.per = shard_bounds(self.num_nodes, rank, world)
         self.n_local = self.hi - self.lo
@@ -141,6 +221,11 @@ class PartitionedGraph:
             self.rowptr, self.col, self.local_edges, self.plan = self._build_sparse(src, dst, n_rows)
             self.rowptr_t, self.col_t, _, self.plan_t = self._build_sparse(dst, src, n_rows)
             return
+        if self.halo == 'peer':
+            self.chunks = 1
+            self.rowptr, self.col, self.local_edges = self._build_peer(src, dst, n_rows)
+            self.rowptr_t, self.col_t, _ = self._build_peer(dst, src, n_rows)
+            return
         self.rowptr, self.col, self.local_edges = self._build(src, dst, n_rows)       # own destinations
         self.rowptr_t, self.col_t, _ = self._build(dst, src, n_rows)                  # own sources (transposed)
 
@@ -152,6 +237,13 @@ class PartitionedGraph:
         rowptr, col, _ = ops.csr_build(torch.stack([plan.col, m], dim=0), n_rows, False)
         plan.col = None                                                   # only the CSR copy is kept
         return rowptr, col, int(m.numel()), plan
+
+    def _build_peer(self, other: Tensor, mine: Tensor, n_rows: int):
+        """CSR over the owned edges whose columns address the owners' published buffers (encode_peer_columns)."""
+        own = (mine >= self.lo) & (mine < self.hi)
+        m = mine[own] - self.lo
+        rowptr, col, _ = ops.csr_build(torch.stack([encode_peer_columns(other[own], self.per), m], dim=0), n_rows, False)
+        return rowptr, col, int(m.numel())
 
     def _build(self, other: Tensor, mine: Tensor, n_rows: int):
         """Sub-CSRs over the edges whose `mine` endpoint this rank owns; columns = `other` endpoints."""
@@ -210,6 +302,10 @@ class PartitionedGraph:
         if self.halo == 'sparse':
             buf = (self.plan_t if transposed else self.plan).exchange(x_local)
             return ops._aggregate_raw(buf, rowptr, col, L.AGG_SUM, x_local, eps, None)
+        if self.halo == 'peer':
+            f = x_local.size(1)
+            table = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).publish(x_local)
+            return ops.aggregate_peer(table, f, rowptr, col, f, x_local, eps)
         pieces = self.gather_pieces_async(x_local)
         out = None
         for c, (work, buf) in enumerate(pieces):

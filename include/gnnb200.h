@@ -234,6 +234,34 @@ int gnnb200_pcgrad_f32(const float* task_grads, float* work, int64_t num_tasks, 
                        const int32_t* order, const int32_t* rank_of, float* out, uint8_t* has_out,
                        int32_t* counters, gnnb200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Node-partitioned aggregation over NVLink peer memory (BASELINE config 5; SURVEY §8e — the reference is
+ * single-device, src/models/gnn.py:41 is the op being sharded).  One process per GPU; every rank publishes its
+ * row shard in a buffer obtained from gnnb200_peer_alloc and maps the other ranks' buffers with
+ * gnnb200_peer_open (CUDA IPC handles, exchanged by the caller over its own channel).  The gather kernel then
+ * reads neighbour rows directly from the owning GPU (SUM mode with the optional (1+eps) self term, same
+ * edge-order accumulation as gnnb200_aggregate_f32), so halo transfer and sums overlap inside one kernel.
+ *   peer_x   : DEVICE array of num_peers device pointers (slot s = base of the row buffer of the rank in slot s,
+ *              all 16-byte aligned with leading dimension ldx); 1 <= num_peers <= GNNB200_MAX_PEERS
+ *   col      : int32 [E_local], encoded (slot << 28) | row_in_that_buffer   (rows < 2^28)
+ * The caller orders the kernel after every rank's publish (a barrier on the stream) and must not overwrite a
+ * published buffer while a peer may still read it (double buffering + one barrier per pass is enough).
+ * gnnb200_peer_alloc / _open / _close / _free are the only entry points that allocate or map memory; they act
+ * on the current device and synchronise like cudaMalloc / cudaFree.
+ * ------------------------------------------------------------------------------------------ */
+#define GNNB200_MAX_PEERS 16
+#define GNNB200_PEER_HANDLE_BYTES 64
+int gnnb200_aggregate_peer_f32(const float* const* peer_x, int num_peers, int64_t ldx, const int32_t* rowptr,
+                               const int32_t* col, int64_t num_rows, int64_t feat, const float* self_x,
+                               int64_t lds, const float* eps, float* out, int64_t ldo, gnnb200_stream_t stream);
+/* stream-ordered copy of this rank's [rows, feat] block into its published buffer */
+int gnnb200_peer_publish_f32(const float* src, int64_t lds, int64_t rows, int64_t feat, float* dst, int64_t ldd,
+                             gnnb200_stream_t stream);
+int gnnb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle /* [GNNB200_PEER_HANDLE_BYTES] */);
+int gnnb200_peer_open(const unsigned char* handle, void** ptr);
+int gnnb200_peer_close(void* ptr);
+int gnnb200_peer_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

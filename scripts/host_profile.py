@@ -76,31 +76,68 @@ def c1_step_factory():
     return step
 
 
+def c4_step_factory():
+    """bench.py's C4 step (sampler draw + pretrain.train_step on four TU-shaped domains, scheme s5)."""
+    import importlib.util
+    import random
+    from gnnb200 import utils
+    spec = importlib.util.spec_from_file_location('bench_for_profile', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    # losses must stay finite under the stubs; zero-filling every output would dominate the profile, so outputs of one
+    # shape share one zero tensor (nothing writes to them here)
+    real_empty, cache = torch.empty, {}
+
+    def shared_zeros(*shape, **k):
+        key = (shape if not (len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size))) else tuple(shape[0]),
+               k.get('dtype'))
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = real_empty(*shape, **k).zero_()
+        return real_empty(0, dtype=t.dtype).set_(t.untyped_storage(), 0, t.shape)     # own version counter
+    ops.torch.empty = shared_zeros
+
+    def coalesce_on_host(edge_index, num_nodes):                    # its result width steers host control flow
+        key = torch.unique(edge_index[0] * num_nodes + edge_index[1])
+        out = torch.zeros_like(edge_index)
+        out[0, :key.numel()], out[1, :key.numel()] = key // num_nodes, key % num_nodes
+        return out, torch.tensor(key.numel())
+    utils.ops.coalesce = coalesce_on_host
+    step, sampler = bench.build_c4_step(torch.device('cpu'), rank=0, world=1)
+    random.seed(1)
+    return lambda: step(sampler.draw())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--profile', action='store_true')
+    ap.add_argument('--only', default=None, choices=[None, 'c1', 'c2', 'c4'])
     args = ap.parse_args()
     torch.set_num_threads(1)
     calls = stub_kernels()
-    for name, factory in (('c1 backbone fwd+bwd (L=3)', c1_step_factory), ('c2 fine-tune step', c2_step_factory)):
+    for name, factory, div in (('c1 backbone fwd+bwd (L=3)', c1_step_factory, 1), ('c2 fine-tune step', c2_step_factory, 1),
+                               ('c4 s5 pre-training step (4 domains x 32 graphs)', c4_step_factory, 10)):
+        if args.only and not name.startswith(args.only):
+            continue
         step = factory()
-        for _ in range(10):
+        steps = max(3, args.steps // div)
+        for _ in range(max(2, 10 // div)):
             step()
         calls['n'] = 0
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
-        dt = (time.perf_counter() - t0) / args.steps
-        per = calls['n'] / args.steps
+        dt = (time.perf_counter() - t0) / steps
+        per = calls['n'] / steps
         print(f'{name}: {dt * 1e3:.3f} ms host time per step, {per:.0f} C-ABI calls -> {dt * 1e6 / max(per, 1):.1f} us per call')
         if args.profile:
             pr = cProfile.Profile()
             pr.enable()
-            for _ in range(args.steps):
+            for _ in range(steps):
                 step()
             pr.disable()
-            pstats.Stats(pr).sort_stats('tottime').print_stats(18)
+            pstats.Stats(pr).sort_stats('tottime').print_stats(30)
 
 
 if __name__ == '__main__':

@@ -110,6 +110,18 @@ BAD = [
     ('gnnb200_pcgrad_f32', (D, D, -1, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, None, 2, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, D, 70000, 10, D, 2, D, D, D, D, D, D, None), L.ERANGE),                       # > 65535 tasks
+    # ---- peer-memory aggregation ----
+    ('gnnb200_aggregate_peer_f32', (None, 2, 256, D, D, 4, 256, None, 0, None, D, 256, None), L.EINVAL),     # no pointer table
+    ('gnnb200_aggregate_peer_f32', (D, 17, 256, D, D, 4, 256, None, 0, None, D, 256, None), L.EINVAL),       # > GNNB200_MAX_PEERS
+    ('gnnb200_aggregate_peer_f32', (D, 2, 256, D, D, 4, 256, None, 0, None, None, 256, None), L.EINVAL),     # out == NULL
+    ('gnnb200_aggregate_peer_f32', (D, 2, 256, D, D, BIG, 256, None, 0, None, D, 256, None), L.ERANGE),
+    ('gnnb200_aggregate_peer_f32', (D, 2, 255, D, D, 4, 255, None, 0, None, D, 256, None), L.EUNSUPPORTED),  # rows not 16-byte
+    ('gnnb200_peer_publish_f32', (D, 128, 4, 256, D, 256, None), L.EINVAL),                                  # lds < feat
+    ('gnnb200_peer_publish_f32', (None, 256, 4, 256, D, 256, None), L.EINVAL),
+    ('gnnb200_peer_alloc', (0, None, None), L.EINVAL),
+    ('gnnb200_peer_open', (None, None), L.EINVAL),
+    ('gnnb200_peer_close', (None,), L.EINVAL),
+    ('gnnb200_peer_free', (None,), L.EINVAL),
 ]
 
 

@@ -1,5 +1,7 @@
 """Neighbour aggregation fwd/bwd against the oracle (CPU scatter_add_ in edge order): bit-exact
 for the sum / (1+eps) self term / transposed backward; 1e-5 for the eps gradient (tree reduce)."""
+import os
+
 import pytest
 import torch
 
@@ -121,3 +123,38 @@ def test_large_graph_properties():
     assert float((zab - (za + zb)).abs().max()) < 1e-3 * float(zab.abs().max())
     # determinism: same bits on a second run
     assert torch.equal(za, ops.gin_aggregate(a, eps, gr.rowptr, gr.col, empty, empty))
+
+
+@pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
+                    reason='peer-memory gather kernel: written after the round-1 GPU budget was spent '
+                           '(set GNNB200_RUN_UNVERIFIED=1)')
+@pytest.mark.parametrize('n,e,f,world', [(1000, 9000, 256, 4), (257, 3000, 128, 8), (2708, 10556, 512, 2),
+                                         (300, 2000, 64, 3), (64, 0, 256, 2), (999, 8000, 1024, 5)])
+def test_peer_gather_equals_single_device(n, e, f, world):
+    """gnnb200_aggregate_peer_f32 with `world` virtual ranks on ONE device: every rank's rows live in their own
+    allocation (different base pointers), columns carry (owner slot, row) — each rank's output must equal its rows
+    of the single-device kernel bit for bit, forward and transposed."""
+    from gnnb200 import partition
+    ei = _graph(n, e, n + 7 * e + f).to(DEV)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(5)).to(DEV)
+    eps = torch.tensor([0.37], device=DEV)
+    gr = Graph(ei, n)
+    want = ops.gin_aggregate(x, eps, gr.rowptr, gr.col, gr.rowptr.new_empty(0), gr.col.new_empty(0))
+    per = (n + world - 1) // world
+    shards = [torch.zeros(per, f, device=DEV) for _ in range(world)]          # the "published buffers"
+    for r, buf in enumerate(shards):
+        lo, hi = r * per, min(n, (r + 1) * per)
+        if hi > lo:
+            buf[: hi - lo] = x[lo:hi]
+    table = torch.tensor([b.data_ptr() for b in shards], dtype=torch.int64, device=DEV)
+    for r in range(world):
+        lo, hi = r * per, min(n, (r + 1) * per)
+        if hi <= lo:
+            continue
+        own = (ei[1] >= lo) & (ei[1] < hi)
+        pairs = torch.stack([partition.encode_peer_columns(ei[0][own], per), ei[1][own] - lo])
+        rowptr, col, _ = ops.csr_build(pairs, hi - lo, False)
+        got = ops.aggregate_peer(table, f, rowptr, col, f, x[lo:hi], eps)
+        assert torch.equal(got, want[lo:hi]), (r, world)
+        no_self = ops.aggregate_peer(table, f, rowptr, col, f, None, None)
+        assert torch.equal(no_self, ops.aggregate(x, gr.rowptr, gr.col, L.AGG_SUM)[lo:hi])

@@ -175,6 +175,130 @@ def _sparse_worker(rank, world, port, n, e, f, locality, out_dir):
         dist.destroy_process_group()
 
 
+class _FakePeerDevice:
+    """CPU emulation of the five peer entry points (include/gnnb200.h) over POSIX shared memory, so that the host
+    logic of the 'peer' halo — handle exchange, pointer tables, two-buffer rotation, column encoding — runs for real
+    across gloo processes.  "Device pointers" are ids into a per-process registry of mapped segments."""
+
+    def __init__(self):
+        from multiprocessing import shared_memory
+        self.shm, self.seg, self.owned = shared_memory, {}, []
+
+    @staticmethod
+    def _floats(ptr, count):
+        import ctypes
+        import numpy as np
+        return np.ctypeslib.as_array((ctypes.c_float * count).from_address(ptr))
+
+    @staticmethod
+    def _ints(ptr, count, ctype):
+        import numpy as np
+        return np.ctypeslib.as_array((ctype * count).from_address(ptr))
+
+    def invoke(self, name, *a):
+        import ctypes
+        import numpy as np
+        if name == 'gnnb200_peer_alloc':
+            nbytes, ptr_ref, handle = a
+            seg = self.shm.SharedMemory(create=True, size=nbytes)
+            self.owned.append(seg)
+            tag = seg.name.encode()
+            assert len(tag) < 64
+            for i in range(64):
+                handle[i] = tag[i] if i < len(tag) else 0
+            key = 1000 + len(self.seg)
+            self.seg[key] = seg
+            ptr_ref._obj.value = key
+            return 0
+        if name == 'gnnb200_peer_open':
+            raw, ptr_ref = a
+            seg = self.shm.SharedMemory(name=bytes(raw).rstrip(b'\0').decode())
+            key = 1000 + len(self.seg)
+            self.seg[key] = seg
+            ptr_ref._obj.value = key
+            return 0
+        if name == 'gnnb200_peer_publish_f32':
+            src, lds, rows, feat, dst, ldd, _ = a
+            view = np.frombuffer(self.seg[dst].buf, dtype=np.float32)
+            view[: rows * ldd].reshape(rows, ldd)[:, :feat] = self._floats(src, rows * lds).reshape(rows, lds)[:, :feat]
+            return 0
+        if name == 'gnnb200_aggregate_peer_f32':
+            table, peers, ldx, rowptr, col, n_rows, feat, self_x, lds, eps, out, ldo, _ = a
+            bases = self._ints(table, peers, ctypes.c_int64)
+            rp = self._ints(rowptr, n_rows + 1, ctypes.c_int32)
+            cols = self._ints(col, int(rp[-1]), ctypes.c_int32).astype(np.int64) & 0xffffffff if rp[-1] else np.zeros(0, np.int64)
+            bufs = [np.frombuffer(self.seg[int(b)].buf, dtype=np.float32) for b in bases]
+            rows_of = [torch.from_numpy(b[: b.size // ldx * ldx].reshape(-1, ldx)[:, :feat].copy()) for b in bufs]
+            gathered = torch.stack([rows_of[int(c) >> 28][int(c) & ((1 << 28) - 1)] for c in cols]) if cols.size else torch.zeros(0, feat)
+            acc = torch.zeros(n_rows, feat)
+            acc.index_add_(0, torch.repeat_interleave(torch.arange(n_rows), torch.from_numpy(np.diff(rp)).long()), gathered)
+            if self_x:
+                mine = torch.from_numpy(self._floats(self_x, n_rows * lds).reshape(n_rows, lds)[:, :feat].copy())
+                acc = acc + (1 + float(self._floats(eps, 1)[0]) if eps else 1.0) * mine
+            self._floats(out, n_rows * ldo).reshape(n_rows, ldo)[:, :feat] = acc.numpy()
+            return 0
+        if name in ('gnnb200_peer_close', 'gnnb200_peer_free'):
+            return 0
+        raise AssertionError(name)
+
+    def release(self):
+        for seg in self.seg.values():
+            seg.close()
+        for seg in self.owned:
+            seg.unlink()
+
+
+def _peer_worker(rank, world, port, n, e, f, out_dir):
+    """halo='peer' end to end on the host: PartitionedGraph(halo='peer').aggregate -> PeerRows (alloc, handle
+    all-gather, open, tables) -> publish + barrier -> encoded-column gather; five passes per direction so that both
+    buffers are reused.  Expected: the rank's rows of the full-graph answer."""
+    from gnnb200 import ops
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    fake = _FakePeerDevice()
+    ops._invoke, ops.on_device, ops._stream = fake.invoke, (lambda t: True), (lambda t: 0)
+
+    def csr_build(pairs, n_rows, by_src):
+        rp, col = _csr(pairs[1], pairs[0], n_rows)
+        return rp.to(torch.int32), col.to(torch.int32), None
+    ops.csr_build = csr_build
+    try:
+        g = torch.Generator().manual_seed(3)
+        ei = torch.randint(0, n, (2, e), generator=g)
+        eps = torch.tensor([0.3])
+        graph = partition.PartitionedGraph(ei, n, rank, world, halo='peer')
+        assert graph.halo == ('peer' if world > 1 else 'dense')
+        lo, hi = graph.lo, graph.hi
+        for it in range(5):
+            x = torch.randn(n, f, generator=g)
+            fwd = torch.zeros(n, f).index_add_(0, ei[1], x[ei[0]]) + (1 + eps) * x
+            bwd = torch.zeros(n, f).index_add_(0, ei[0], x[ei[1]]) + (1 + eps) * x
+            for transposed, want in ((False, fwd), (True, bwd)):
+                got = graph.aggregate(x[lo:hi].contiguous(), eps, transposed)
+                assert torch.allclose(got, want[lo:hi], rtol=0, atol=1e-5), (it, transposed)
+        rows = partition.PeerRows.get(graph.per, f, rank, world, None, x.device)
+        assert rows.turn == 10 and tuple(rows.tables.shape) == (2, world)
+        dist.barrier()
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.barrier()
+        fake.release()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,e', [(2, 101, 700), (3, 50, 400), (2, 7, 5)])
+def test_peer_halo_host_logic(tmp_path, world, n, e):
+    mp.spawn(_peer_worker, args=(world, _free_port(), n, e, 8, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+def test_encode_peer_columns():
+    ids = torch.tensor([0, 5, 99, 100, 101, 799])
+    code = partition.encode_peer_columns(ids, 100)
+    assert code.tolist() == [0, 5, 99, 1 << 28, (1 << 28) | 1, (7 << 28) | 99]
+    assert int(code.max()) < 2 ** 31                                     # 8 ranks fit the int32 CSR column
+
+
 @pytest.mark.parametrize('world,n,e,locality', [(2, 101, 700, 0.0), (3, 101, 400, 0.95), (2, 7, 5, 0.0), (3, 2, 6, 0.0)])
 def test_sparse_halo_plan_and_exchange(tmp_path, world, n, e, locality):
     mp.spawn(_sparse_worker, args=(world, _free_port(), n, e, 8, locality, str(tmp_path)), nprocs=world, join=True)
