@@ -78,6 +78,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// TMA store of one shared-memory box (bulk async-group completion): the epilogue's TMA_ST variant
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING shared memory (the tile may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -159,9 +170,15 @@ struct TileCfg {
   static_assert(kStages >= 2, "tile does not fit shared memory");
 };
 
-template <int BN, bool A_MN, bool B_MN, bool X3>
+// TMA_ST (opt-in, GNNB200_GEMM_TMA_STORE=1; plain tf32, no split-K, no residual, no fused statistics): the epilogue's
+// XOR-swizzled 32x32 staging tile IS the SWIZZLE_128B box layout, so instead of reading it back and issuing
+// st.global the warp applies bias/ReLU on the TMEM side, and one lane hands the tile to the TMA unit
+// (cp.async.bulk.tensor store, clipped at the matrix edge by the tensor map).
+template <int BN, bool A_MN, bool B_MN, bool X3, bool TMA_ST = false>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const Params p) {
+  static_assert(!(TMA_ST && X3), "the TMA-store epilogue exists for the plain tf32 kernel only");
   using Cfg = TileCfg<BN, X3>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kABytes = Cfg::kABytes;
@@ -187,6 +204,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    if constexpr (TMA_ST) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_c) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -360,6 +378,39 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
+      if constexpr (TMA_ST) {
+#pragma unroll 1
+        for (int c = c_begin; c < (p.debug == 2 ? c_begin : c_end); ++c) {
+          if (lane == 0) tma_store_wait_read();          // the previous chunk's store has drained the staging tile
+          __syncwarp();
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                   __uint_as_float(v[j + 3]));
+            if (p.bias && col0 + j < p.N) {               // warp-uniform address: one broadcast load
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(stage + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = o;
+          }
+          if (c + 1 < c_end) {                           // next chunk's TMEM load overlaps this chunk's store
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + (c + 1) * 32), v);
+          } else {                                       // accumulator fully read: hand TMEM back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0 && p.debug != 1) {
+            tma_store_2d(&map_c, stage, col0, m0 + q * 32);                // rows >= M / columns >= N are clipped
+            tma_store_commit();
+          }
+        }
+      } else {   // st.global epilogue (body below keeps its indentation)
 #pragma unroll 1
       for (int c = c_begin; c < (p.debug == 2 ? c_begin : c_end); ++c) {
         const int col = n0 + c * 32 + c4;
@@ -455,7 +506,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         __syncwarp();                                   // the staging tile is reused by the next chunk
       }
+      }   // !TMA_ST
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (TMA_ST) {
+      if (lane == 0) tma_store_wait_read();              // shared memory must outlive the last store's reads
     }
   }
 
@@ -549,26 +604,37 @@ static int pick_bn(long long N, bool x3) {
   return 64;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool X3>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, bool X3, bool TMA_ST>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p, int grid,
+                  cudaStream_t stream) {
   constexpr size_t smem = TileCfg<BN, X3>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
-    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  gemm_tf32_kernel<BN, A_MN, B_MN, X3><<<grid, kThreads, smem, stream>>>(ma, mb, p);
+  gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST><<<grid, kThreads, smem, stream>>>(ma, mb, mc, p);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
 
-template <int BN, bool X3>
-static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid,
-                     cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<BN, false, false, X3>(ma, mb, p, grid, stream);
-  if (!a_mn && b_mn) return launch<BN, false, true, X3>(ma, mb, p, grid, stream);
-  if (a_mn && !b_mn) return launch<BN, true, false, X3>(ma, mb, p, grid, stream);
-  return launch<BN, true, true, X3>(ma, mb, p, grid, stream);
+template <int BN, bool X3, bool TMA_ST = false>
+static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                     const Params& p, int grid, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<BN, false, false, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
+  if (!a_mn && b_mn) return launch<BN, false, true, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
+  if (a_mn && !b_mn) return launch<BN, true, false, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
+  return launch<BN, true, true, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
+}
+
+// GNNB200_GEMM_TMA_STORE=1: TMA-store epilogue for the GEMMs it covers (read once; opt-in until measured)
+static bool tma_store_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GNNB200_GEMM_TMA_STORE");
+    return e && atoi(e) != 0;
+  }();
+  return on;
 }
 
 }  // namespace tc
@@ -646,13 +712,24 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   }
   const long long total = tiles * splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+  // TMA-store epilogue: C as a tensor map of 32x32 boxes in the staging tile's swizzle (inner = N, outer = M)
+  const bool tma_st = !x3 && splits == 1 && !p.residual && !p.col_part && tma_store_enabled();
+  CUtensorMap mc = ma;                                   // unused unless tma_st
+  if (tma_st) {
+    rc = make_map(&mc, C, N, M, ldc, 32, false);
+    if (rc) return rc;
+  }
   if (x3) {
-    if (bn == 128) rc = launch_bn<128, true>(a_mn, b_mn, ma, mb, p, grid, stream);
-    else rc = launch_bn<64, true>(a_mn, b_mn, ma, mb, p, grid, stream);
+    if (bn == 128) rc = launch_bn<128, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    else rc = launch_bn<64, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+  } else if (tma_st) {
+    if (bn == 256) rc = launch_bn<256, false, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, false, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    else rc = launch_bn<64, false, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
   } else {
-    if (bn == 256) rc = launch_bn<256, false>(a_mn, b_mn, ma, mb, p, grid, stream);
-    else if (bn == 128) rc = launch_bn<128, false>(a_mn, b_mn, ma, mb, p, grid, stream);
-    else rc = launch_bn<64, false>(a_mn, b_mn, ma, mb, p, grid, stream);
+    if (bn == 256) rc = launch_bn<256, false>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, false>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    else rc = launch_bn<64, false>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
   }
   if (rc) return rc;
   if (splits > 1) {
