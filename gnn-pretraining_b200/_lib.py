@@ -4,7 +4,7 @@ There is no CPU or eager fallback: if the shared library is missing, loading fai
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint64, c_void_p, POINTER, Structure
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libgnnb200.so')
@@ -19,6 +19,21 @@ EPI_NONE, EPI_RELU = 0, 1
 P = c_void_p
 I64 = c_int64
 SZP = POINTER(c_size_t)
+
+
+
+class GinLayerArgs(Structure):
+    """gnnb200_gin_layer_t of include/gnnb200.h (field for field)."""
+    _fields_ = ([('num_rows', I64), ('hidden', I64), ('mid', I64), ('rowptr', P), ('col', P), ('h', P), ('ldh', I64),
+                 ('eps', P)] +
+                [(k, P) for k in ('w1', 'b1', 'gamma1', 'beta1', 'w2', 'b2', 'gamma2', 'beta2',
+                                  'running_mean1', 'running_var1', 'running_mean2', 'running_var2',
+                                  'mean1', 'invstd1', 'mean2', 'invstd2', 'z', 'a1', 'r1', 's', 'out', 'grad_out',
+                                  'ds', 'dr1', 'da1', 'dz', 'dw1', 'dw2', 'dgamma1', 'dbeta1', 'dgamma2', 'dbeta2', 'deps')] +
+                [('seed', c_uint64), ('drop_p', c_float), ('momentum1', c_float), ('bn_eps1', c_float),
+                 ('momentum2', c_float), ('bn_eps2', c_float), ('training', c_int), ('precision', c_int),
+                 ('need_dh', c_int)])
+
 
 # name -> argtypes, in the order of include/gnnb200.h
 SIGNATURES = {
@@ -54,7 +69,13 @@ SIGNATURES = {
     'gnnb200_peer_open': [P, POINTER(c_void_p)],
     'gnnb200_peer_close': [P],
     'gnnb200_peer_free': [P],
+    'gnnb200_gin_layer_fwd_f32': [POINTER(GinLayerArgs), P, SZP, P],
+    'gnnb200_gin_layer_bwd_f32': [POINTER(GinLayerArgs), P, SZP, P],
+    'gnnb200_dev_trace_begin': [P, c_size_t],
+    'gnnb200_dev_trace_end': [],
 }
+TRACE_FUNCTIONS = ('gnnb200_aggregate_f32', 'gnnb200_gemm_f32', 'gnnb200_colstats_f32', 'gnnb200_bn_finalize_f32',
+                   'gnnb200_bn_act_fwd_f32', 'gnnb200_bn_act_bwd_f32', 'gnnb200_dot_f32')   # ids of gnnb200_dev_trace_*
 PEER_SHIFT, MAX_PEERS, PEER_HANDLE_BYTES = 28, 16, 64
 
 _lib = None
@@ -76,7 +97,8 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError -> header and library disagree
         fn.argtypes = argtypes
-        fn.restype = c_char_p if name == 'gnnb200_error_string' else c_int
+        fn.restype = (c_char_p if name == 'gnnb200_error_string' else
+                      c_longlong if name == 'gnnb200_dev_trace_end' else c_int)
     _lib = lib
     return lib
 

@@ -81,6 +81,9 @@ KERNELS_PER_CALL = {
     'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,
     'gnnb200_aggregate_peer_f32': 1, 'gnnb200_peer_publish_f32': 0, 'gnnb200_peer_alloc': 0, 'gnnb200_peer_open': 0,
     'gnnb200_peer_close': 0, 'gnnb200_peer_free': 0,
+    # composites (csrc/gin_layer.cu): base sequence + optional parts counted under their own keys by gnnb200/fused.py
+    'gnnb200_gin_layer_fwd_f32': 5, 'gnnb200_gin_layer_fwd_f32:stats': 6,
+    'gnnb200_gin_layer_bwd_f32': 10, 'gnnb200_gin_layer_bwd_f32:deps': 2, 'gnnb200_gin_layer_bwd_f32:dh': 1,
 }
 _calls = {}
 AGG_TIMER = None      # bench.py sets this to a list to collect (start, stop) CUDA events per aggregation launch

@@ -262,6 +262,47 @@ int gnnb200_peer_open(const unsigned char* handle, void** ptr);
 int gnnb200_peer_close(void* ptr);
 int gnnb200_peer_free(void* ptr);
 
+/* ------------------------------------------------------------------------------------------
+ * One call per GIN layer pass (GINLayer.forward of src/models/gnn.py:26-43 and its backward): the launch
+ * sequence gather(+self term) -> Linear -> BatchNorm+ReLU -> Linear(+h) -> BatchNorm+ReLU+dropout issued from
+ * C++ on the caller's stream.  Every step is one of the entry points above with the arguments documented
+ * there; the only difference to calling them one by one is host time (one FFI crossing per layer pass).
+ *   fwd: reads h, eps, the parameters and (eval mode, training == 0) mean1..invstd2; writes z, a1, r1, s, out and
+ *        (training) mean1..invstd2 + the running buffers (may be NULL).
+ *   bwd: training mode only (GNNB200_EUNSUPPORTED otherwise); rowptr/col are the by-SOURCE CSR; reads grad_out and
+ *        what fwd saved; writes ds (which becomes dh when need_dh: the transposed gather accumulates into it), dr1,
+ *        da1, dz, dw1 [mid, hidden], dw2 [hidden, mid], dgamma1..dbeta2, and deps (NULL = not wanted; needs ldh == hidden).
+ *        The bias gradients are identically zero in training mode (a bias feeding BatchNorm) and are not written.
+ * All activations are dense row-major (leading dimension = width) except h (ldh).  Workspace query as everywhere.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gnnb200_gin_layer {
+  int64_t num_rows, hidden, mid;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* h;
+  int64_t ldh;
+  const float* eps;
+  const float *w1, *b1, *gamma1, *beta1, *w2, *b2, *gamma2, *beta2;
+  float *running_mean1, *running_var1, *running_mean2, *running_var2;
+  float *mean1, *invstd1, *mean2, *invstd2;
+  float *z, *a1, *r1, *s, *out;
+  const float* grad_out;
+  float *ds, *dr1, *da1, *dz;
+  float *dw1, *dw2, *dgamma1, *dbeta1, *dgamma2, *dbeta2, *deps;
+  uint64_t seed;
+  float drop_p, momentum1, bn_eps1, momentum2, bn_eps2;
+  int training, precision, need_dh;
+} gnnb200_gin_layer_t;
+int gnnb200_gin_layer_fwd_f32(const gnnb200_gin_layer_t* layer, void* workspace, size_t* workspace_bytes,
+                              gnnb200_stream_t stream);
+int gnnb200_gin_layer_bwd_f32(const gnnb200_gin_layer_t* layer, void* workspace, size_t* workspace_bytes,
+                              gnnb200_stream_t stream);
+/* Development hook (per thread): between _begin and _end the two composites record the calls they would make as
+ * 64-bit words (function id, argument count, arguments) instead of making them; _end returns the word count
+ * (-1 = buffer too small).  Function ids: 0 aggregate, 1 gemm, 2 colstats, 3 bn_finalize, 4 bn_act_fwd, 5 bn_act_bwd, 6 dot. */
+int gnnb200_dev_trace_begin(uint64_t* buf, size_t capacity_words);
+long long gnnb200_dev_trace_end(void);
+
 #ifdef __cplusplus
 }
 #endif
