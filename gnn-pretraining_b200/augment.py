@@ -32,6 +32,7 @@ class _ViewPlan:
     """Host-side description of one augmented view of the whole batch."""
 
     def __init__(self):
+        self.total = 0                            # nodes of the view batch so far
         self.node_ids: List[np.ndarray] = []      # global ids of kept nodes, per graph (ascending)
         self.edges: List[np.ndarray] = []         # [2, e'] relabelled + offset into the view batch, per graph
         self.sizes: List[int] = []
@@ -39,7 +40,8 @@ class _ViewPlan:
         self.kept_local: List[np.ndarray] = []
 
     def add(self, start: int, kept: np.ndarray, edges: np.ndarray, feat_cols, num_feats: int):
-        offset = sum(self.sizes)
+        offset = self.total
+        self.total += int(kept.size)
         self.node_ids.append(kept + start)
         self.edges.append(edges + offset)
         if feat_cols is not None and kept.size:
@@ -127,9 +129,13 @@ class GraphAugmentor:
                 kept, edges, feat_cols = _plan_view(n, local, num_feats, generator)
                 plan.add(start, kept, edges, feat_cols, num_feats)
                 views.append(kept)
-            # augmentations.py:77-85: nodes present in both views
-            masks_a.append(np.isin(views[0], views[1]))
-            masks_b.append(np.isin(views[1], views[0]))
+            # augmentations.py:77-85: nodes present in both views (membership through a per-graph bitmap: the kept
+            # sets are subsets of range(n), so this is isin() without its sort/concatenate machinery)
+            in_a, in_b = np.zeros(n, dtype=bool), np.zeros(n, dtype=bool)
+            in_a[views[0]] = True
+            in_b[views[1]] = True
+            masks_a.append(in_b[views[0]])
+            masks_b.append(in_a[views[1]])
         v1, v2 = plans[0].build(x), plans[1].build(x)
         # all masks travel in one upload and are handed back as per-graph views of it
         def to_device(masks):
