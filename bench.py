@@ -8,7 +8,7 @@ InputEncoder + 5-layer GIN backbone in TRAIN mode (BatchNorm batch statistics, d
 loss = h.sum(), backward, AdamW step.  One step = CSR+CSC build from edge_index, forward,
 backward, optimizer.  metric = aggregated edges/sec = E * L * 2 (fwd + bwd sweeps) / step time.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S] [--locality P] [--halo dense|sparse|auto|peer]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S] [--locality P] [--halo dense|sparse|auto|peer|peercopy]
   python bench.py --workload c4 ...      BASELINE configs[3]: data-parallel s5 pre-training step (steps/s, weak scaling)
 
 N > 1 (launched by torch.distributed.run): the same graph node-partitioned into N contiguous
@@ -295,7 +295,8 @@ def run_product(args):
                        'edge_locality': args.locality, 'gemm_precision': gnn.default_precision(),
                        'l2_policy': 'inputs_larger_than_L2 (2.5 GB activations per layer vs 126 MB L2)',
                        'parallelism': 'single' if world == 1 else f'node_partition{world}+' + (
-                           {'sparse': 'halo_alltoall_sparse', 'peer': 'halo_read_in_gather_over_nvlink_peer_memory'}.get(
+                           {'sparse': 'halo_alltoall_sparse', 'peer': 'halo_read_in_gather_over_nvlink_peer_memory',
+                            'peercopy': 'halo_allgather_by_copy_engines'}.get(
                                runner.last_halo, 'halo_allgather'))},
             'clocks': clocks.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms,
@@ -619,7 +620,7 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C5 graph (debug only; 1.0 = BASELINE config)')
     ap.add_argument('--locality', type=float, default=0.0, help='fraction of intra-block edges (0 = uniform random)')
     ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3'])
-    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'auto', 'peer'],
+    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'auto', 'peer', 'peercopy'],
                     help='N > 1: rows exchanged per layer (default dense = all-gather; see gnnb200/partition.py)')
     ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -65,6 +65,7 @@ SIGNATURES = {
     'gnnb200_pcgrad_f32': [P, P, I64, I64, P, I64, P, P, P, P, P, P, P],
     'gnnb200_aggregate_peer_f32': [P, c_int, I64, P, P, I64, I64, P, I64, P, P, I64, P],
     'gnnb200_peer_publish_f32': [P, I64, I64, I64, P, I64, P],
+    'gnnb200_peer_copy_f32': [P, P, I64, P],
     'gnnb200_peer_alloc': [c_size_t, POINTER(c_void_p), P],
     'gnnb200_peer_open': [P, POINTER(c_void_p)],
     'gnnb200_peer_close': [P],

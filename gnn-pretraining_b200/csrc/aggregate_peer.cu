@@ -133,6 +133,15 @@ extern "C" int gnnb200_peer_publish_f32(const float* src, int64_t lds, int64_t r
   return GNNB200_OK;
 }
 
+// Pull a peer's published block into local memory with the copy engines (no SM time): the 'peercopy' exchange.
+extern "C" int gnnb200_peer_copy_f32(float* dst, const float* src, int64_t count, gnnb200_stream_t stream_) {
+  if (count < 0) return GNNB200_EINVAL;
+  if (count == 0) return GNNB200_OK;
+  if (!dst || !src) return GNNB200_EINVAL;
+  GNNB200_CHECK_CUDA(cudaMemcpyAsync(dst, src, (size_t)count * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream_));
+  return GNNB200_OK;
+}
+
 // ---- peer-mapped buffers (CUDA IPC; the only entry points of the library that allocate) -------------------
 
 static_assert(sizeof(cudaIpcMemHandle_t) == GNNB200_PEER_HANDLE_BYTES, "handle size");

@@ -79,7 +79,7 @@ KERNELS_PER_CALL = {
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
     'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,
-    'gnnb200_aggregate_peer_f32': 1, 'gnnb200_peer_publish_f32': 0, 'gnnb200_peer_alloc': 0, 'gnnb200_peer_open': 0,
+    'gnnb200_aggregate_peer_f32': 1, 'gnnb200_peer_publish_f32': 0, 'gnnb200_peer_copy_f32': 0, 'gnnb200_peer_alloc': 0, 'gnnb200_peer_open': 0,
     'gnnb200_peer_close': 0, 'gnnb200_peer_free': 0,
     # composites (csrc/gin_layer.cu): base sequence + optional parts counted under their own keys by gnnb200/fused.py
     'gnnb200_gin_layer_fwd_f32': 5, 'gnnb200_gin_layer_fwd_f32:stats': 6,

@@ -47,13 +47,16 @@ DEFAULT_HALO_CHUNKS = 1
 #              (gnnb200_aggregate_peer_f32) — transfer and sums overlap inside ONE kernel, nothing is packed, staged
 #              or all-gathered; per pass one local copy of the shard and one barrier.  A remote row crosses NVLink once
 #              per referencing edge, so this is for graphs with locality; same per-row edge order => same bits.
+#   'peercopy': the dense exchange without NCCL: every rank publishes its shard (PeerRows) and PULLS the other shards with
+#              the copy engines (cudaMemcpyAsync from the peer-mapped buffers, no SM time, no NCCL kernel sharing HBM with
+#              anything), then runs the ordinary gather on the assembled [P * rows, F] buffer.  Same bytes as 'dense'.
 # 'sparse'/'auto' are covered by the gloo world-2 tests (index plan, exchange, algebra) but were written after the
 # round's GPU budget was spent: unmeasured on NCCL, hence opt-in (GNNB200_HALO or the `halo=` argument).
 # 'peer' was written at the same time; its kernel and column encoding are tested on one GPU against the
 # single-device kernel (virtual ranks = slices of one buffer), the IPC leg needs 2 GPUs and is equally unmeasured.
 DEFAULT_HALO = 'dense'
 SPARSE_HALO_MAX_FRACTION = 0.5
-HALO_MODES = ('dense', 'sparse', 'auto', 'peer')
+HALO_MODES = ('dense', 'sparse', 'auto', 'peer', 'peercopy')
 
 
 def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
@@ -162,8 +165,20 @@ class PeerRows:
                 self._mapped.append(ptr.value or 0)
                 ptrs.append(ptr.value or 0)
             tables.append(ptrs)
+        self.ptrs = tables                                                         # the same pointers on the host
         self.tables = torch.tensor(tables, dtype=torch.int64).to(device)          # [2, P] base pointers
         self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def gather_all(self, x_local: Tensor) -> Tensor:
+        """[P * rows, F]: every rank's published shard pulled by the copy engines (the 'peercopy' exchange)."""
+        self.publish(x_local)
+        b = (self.turn - 1) & 1
+        full = x_local.new_empty(self.world * self.rows, self.feat)
+        count, stream = self.rows * self.feat, ops._stream(x_local)
+        for r in range(self.world):
+            L.check(ops._invoke('gnnb200_peer_copy_f32', full.data_ptr() + 4 * r * count, self.ptrs[b][r], count, stream),
+                    f'peer_copy (rank {r})')
+        return full
 
     def publish(self, x_local: Tensor) -> Tensor:
         b = self.turn & 1
@@ -210,6 +225,9 @@ class PartitionedGraph:
         self.rpc = (self.per + self.chunks - 1) // self.chunks            # rows per piece of one shard
         n_rows = max(self.n_local, 1)
         src, dst = edge_index[0], edge_index[1]
+        if halo == 'peercopy':
+            self.chunks = 1                                               # one exchange, one gather pass
+            self.rpc = self.per
         if world > 1 and halo == 'auto':
             own = (dst >= self.lo) & (dst < self.hi)
             frac = remote_fraction_needed(src[own], self.lo, self.hi, self.num_nodes, group)
@@ -306,6 +324,10 @@ class PartitionedGraph:
             f = x_local.size(1)
             table = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).publish(x_local)
             return ops.aggregate_peer(table, f, rowptr, col, f, x_local, eps)
+        if self.halo == 'peercopy':
+            f = x_local.size(1)
+            full = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).gather_all(x_local)
+            return ops._aggregate_raw(full, rowptr, col, L.AGG_SUM, x_local, eps, None)
         pieces = self.gather_pieces_async(x_local)
         out = None
         for c, (work, buf) in enumerate(pieces):

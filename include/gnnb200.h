@@ -257,6 +257,8 @@ int gnnb200_aggregate_peer_f32(const float* const* peer_x, int num_peers, int64_
 /* stream-ordered copy of this rank's [rows, feat] block into its published buffer */
 int gnnb200_peer_publish_f32(const float* src, int64_t lds, int64_t rows, int64_t feat, float* dst, int64_t ldd,
                              gnnb200_stream_t stream);
+/* stream-ordered copy of `count` floats from a (peer-mapped or local) buffer: the copy-engine all-gather of 'peercopy' */
+int gnnb200_peer_copy_f32(float* dst, const float* src, int64_t count, gnnb200_stream_t stream);
 int gnnb200_peer_alloc(size_t bytes, void** ptr, unsigned char* handle /* [GNNB200_PEER_HANDLE_BYTES] */);
 int gnnb200_peer_open(const unsigned char* handle, void** ptr);
 int gnnb200_peer_close(void* ptr);

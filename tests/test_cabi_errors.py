@@ -118,6 +118,8 @@ BAD = [
     ('gnnb200_aggregate_peer_f32', (D, 2, 255, D, D, 4, 255, None, 0, None, D, 256, None), L.EUNSUPPORTED),  # rows not 16-byte
     ('gnnb200_peer_publish_f32', (D, 128, 4, 256, D, 256, None), L.EINVAL),                                  # lds < feat
     ('gnnb200_peer_publish_f32', (None, 256, 4, 256, D, 256, None), L.EINVAL),
+    ('gnnb200_peer_copy_f32', (D, None, 16, None), L.EINVAL),
+    ('gnnb200_peer_copy_f32', (D, D, -1, None), L.EINVAL),
     ('gnnb200_peer_alloc', (0, None, None), L.EINVAL),
     ('gnnb200_peer_open', (None, None), L.EINVAL),
     ('gnnb200_peer_close', (None,), L.EINVAL),

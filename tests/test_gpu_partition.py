@@ -164,13 +164,15 @@ def _peer_worker(rank, world, port, out_dir):
         eps = torch.tensor([0.25], device=dev)
         dense = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='dense', chunks=1)
         peer = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='peer')
+        pull = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='peercopy')
         # several passes in a row with fresh values: exercises the two-buffer rotation and the per-pass barrier
         for it in range(5):
             x = torch.randn(n, 256, generator=torch.Generator().manual_seed(4 + it)).to(dev)
             for transposed in (False, True):
                 a = dense.aggregate(x[dense.lo:dense.hi].contiguous(), eps, transposed)
                 b = peer.aggregate(x[peer.lo:peer.hi].contiguous(), eps, transposed)
-                assert torch.equal(a, b), (it, transposed)          # same edge order per row => same bits
+                c = pull.aggregate(x[pull.lo:pull.hi].contiguous(), eps, transposed)
+                assert torch.equal(a, b) and torch.equal(a, c), (it, transposed)   # same edge order per row => same bits
         torch.cuda.synchronize()
         dist.barrier()
         for rows in list(partition.PeerRows._cache.values()):

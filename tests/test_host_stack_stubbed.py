@@ -153,7 +153,7 @@ def _partition_worker(rank, world, port, halo, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('halo,world', [('dense', 2), ('sparse', 2), ('auto', 3), ('peer', 2)])
+@pytest.mark.parametrize('halo,world', [('dense', 2), ('sparse', 2), ('auto', 3), ('peer', 2), ('peercopy', 2)])
 def test_partitioned_step_host_logic_over_gloo(tmp_path, halo, world):
     import socket
     import torch.multiprocessing as mp

@@ -237,6 +237,24 @@ class _FakePeerDevice:
                 acc = acc + (1 + float(self._floats(eps, 1)[0]) if eps else 1.0) * mine
             self._floats(out, n_rows * ldo).reshape(n_rows, ldo)[:, :feat] = acc.numpy()
             return 0
+        if name == 'gnnb200_peer_copy_f32':
+            dst, src, count, _ = a
+            self._floats(dst, count)[:] = np.frombuffer(self.seg[src].buf, dtype=np.float32)[:count]
+            return 0
+        if name == 'gnnb200_aggregate_f32':                      # the ordinary single-buffer gather ('peercopy' ends in it)
+            x, ldx, rowptr, col, n_rows, feat, mode, self_x, lds, eps, dinv, out, ldo, _ = a
+            assert mode == 0 and not dinv
+            rp = self._ints(rowptr, n_rows + 1, ctypes.c_int32)
+            cols = self._ints(col, int(rp[-1]), ctypes.c_int32).astype(np.int64) if rp[-1] else np.zeros(0, np.int64)
+            rows_x = int(cols.max()) + 1 if cols.size else 0
+            xs = torch.from_numpy(self._floats(x, max(rows_x, 1) * ldx).reshape(-1, ldx)[:, :feat].copy())
+            acc = torch.zeros(n_rows, feat)
+            acc.index_add_(0, torch.repeat_interleave(torch.arange(n_rows), torch.from_numpy(np.diff(rp)).long()),
+                           xs[torch.from_numpy(cols)] if cols.size else torch.zeros(0, feat))
+            mine = torch.from_numpy(self._floats(self_x, n_rows * lds).reshape(n_rows, lds)[:, :feat].copy())
+            acc = acc + (1 + float(self._floats(eps, 1)[0])) * mine
+            self._floats(out, n_rows * ldo).reshape(n_rows, ldo)[:, :feat] = acc.numpy()
+            return 0
         if name in ('gnnb200_peer_close', 'gnnb200_peer_free'):
             return 0
         raise AssertionError(name)
@@ -248,8 +266,8 @@ class _FakePeerDevice:
             seg.unlink()
 
 
-def _peer_worker(rank, world, port, n, e, f, out_dir):
-    """halo='peer' end to end on the host: PartitionedGraph(halo='peer').aggregate -> PeerRows (alloc, handle
+def _peer_worker(rank, world, port, n, e, f, out_dir, halo='peer'):
+    """halo='peer' / 'peercopy' end to end on the host: PartitionedGraph(halo='peer').aggregate -> PeerRows (alloc, handle
     all-gather, open, tables) -> publish + barrier -> encoded-column gather; five passes per direction so that both
     buffers are reused.  Expected: the rank's rows of the full-graph answer."""
     from gnnb200 import ops
@@ -266,8 +284,8 @@ def _peer_worker(rank, world, port, n, e, f, out_dir):
         g = torch.Generator().manual_seed(3)
         ei = torch.randint(0, n, (2, e), generator=g)
         eps = torch.tensor([0.3])
-        graph = partition.PartitionedGraph(ei, n, rank, world, halo='peer')
-        assert graph.halo == ('peer' if world > 1 else 'dense')
+        graph = partition.PartitionedGraph(ei, n, rank, world, halo=halo)
+        assert graph.halo == (halo if world > 1 else 'dense')
         lo, hi = graph.lo, graph.hi
         for it in range(5):
             x = torch.randn(n, f, generator=g)
@@ -286,9 +304,10 @@ def _peer_worker(rank, world, port, n, e, f, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('halo', ['peer', 'peercopy'])
 @pytest.mark.parametrize('world,n,e', [(2, 101, 700), (3, 50, 400), (2, 7, 5)])
-def test_peer_halo_host_logic(tmp_path, world, n, e):
-    mp.spawn(_peer_worker, args=(world, _free_port(), n, e, 8, str(tmp_path)), nprocs=world, join=True)
+def test_peer_halo_host_logic(tmp_path, world, n, e, halo):
+    mp.spawn(_peer_worker, args=(world, _free_port(), n, e, 8, str(tmp_path), halo), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
 
 
