@@ -15,7 +15,9 @@ Batches are identical, tensor for tensor, to `Batch.from_data_list([dataset[i] f
 changes no result (tests/test_loader.py pins both on CPU against the reference's classes over the PyG shim).
 Everything here is device-agnostic tensor plumbing in front of the kernels.
 """
-from typing import Dict, Iterator, List, Optional, Sequence
+import os
+from pathlib import Path
+from typing import Dict, Iterator, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
@@ -229,3 +231,87 @@ class LinkBatches:
     def __iter__(self):
         for lo in range(0, self.edges.size(1), self.batch_size):
             yield self.data, self.edges[:, lo:lo + self.batch_size], self.labels[lo:lo + self.batch_size]
+
+
+# ---- the reference's on-disk format and loader factories (src/data/data_setup.py:63-72, pretrain_data_loaders.py:49-83,
+# finetune_data_loaders.py:68-119) -----------------------------------------------------------------------------------------
+# data/processed/<domain>/{data.pt = [Data, ...], splits.pt = {split: indices | edges}, graph_properties.pt = [G, 12]}, written
+# with torch.save.  The pickles name `torch_geometric.data.Data`: they load with PyG installed or over gnnb200.compat (the
+# package's own torch_geometric stand-in); either kind of Data object is accepted by ResidentDomain.  Same function names,
+# argument order and iteration order as the reference; `device` / `root` are additions with defaults.
+
+PROCESSED_DIR = Path(os.environ.get('GNNB200_PROCESSED_DIR', Path('data') / 'processed'))
+
+
+def _domain_dir(domain_name: str, root) -> Path:
+    return Path(root if root is not None else PROCESSED_DIR) / domain_name
+
+
+def save_processed_data(dataset_name: str, data: List, splits: Dict[str, Tensor], graph_properties: Optional[Tensor] = None,
+                        root=None) -> None:
+    """data_setup.py:66-72."""
+    save_dir = _domain_dir(dataset_name, root)
+    os.makedirs(save_dir, exist_ok=True)
+    torch.save(data, save_dir / 'data.pt')
+    torch.save(splits, save_dir / 'splits.pt')
+    if graph_properties is not None:
+        torch.save(graph_properties, save_dir / 'graph_properties.pt')
+
+
+def _load_domain(domain_name: str, root, with_properties_for: Optional[str] = None):
+    domain_dir = _domain_dir(domain_name, root)
+    graphs = torch.load(domain_dir / 'data.pt', weights_only=False)
+    splits = torch.load(domain_dir / 'splits.pt', weights_only=False)
+    if with_properties_for is not None:                       # pretrain_data_loaders.py:49-53
+        properties = torch.load(domain_dir / 'graph_properties.pt', weights_only=False)
+        for idx in splits[with_properties_for]:
+            graphs[int(idx)].graph_properties = properties[int(idx)]
+    return graphs, splits
+
+
+def create_train_data_loader(domains: List[str], generator: torch.Generator, device: Optional[torch.device] = None,
+                             root=None) -> BalancedMultiDomainSampler:
+    """pretrain_data_loaders.py:69-83."""
+    sets = {}
+    for domain in domains:
+        graphs, splits = _load_domain(domain, root, 'train')
+        sets[domain] = GraphDataset(graphs, splits['train'])
+    return BalancedMultiDomainSampler(sets, generator, device=device)
+
+
+def create_val_data_loader(domain_name: str, generator: torch.Generator, device: Optional[torch.device] = None, root=None
+                           ) -> List[Batch]:
+    """pretrain_data_loaders.py:56-66 (the reference's PyG DataLoader does not shuffle: consecutive slices)."""
+    graphs, splits = _load_domain(domain_name, root, 'val')
+    return sequential_batches(GraphDataset(graphs, splits['val']), BATCH_SIZE, device)
+
+
+def create_graph_classification_loader(domain_name: str, split: str, batch_size: int, generator: torch.Generator,
+                                       device: Optional[torch.device] = None, root=None) -> List[Batch]:
+    """finetune_data_loaders.py:68-78."""
+    graphs, splits = _load_domain(domain_name, root)
+    return sequential_batches(GraphDataset(graphs, splits[split]), batch_size, device)
+
+
+def create_node_classification_loader(domain_name: str, split: str, batch_size: int, generator: torch.Generator,
+                                      device: Optional[torch.device] = None, root=None) -> NodeBatches:
+    """finetune_data_loaders.py:81-95."""
+    graphs, splits = _load_domain(domain_name, root)
+    return NodeBatches(graphs[0], splits[split], batch_size, device)
+
+
+def create_link_prediction_loader(domain_name: str, split: str, batch_size: int, generator: torch.Generator,
+                                  device: Optional[torch.device] = None, root=None) -> LinkBatches:
+    """finetune_data_loaders.py:98-107."""
+    graphs, splits = _load_domain(domain_name, root)
+    return LinkBatches(graphs[0], splits, split, batch_size, device)
+
+
+def create_finetune_data_loader(domain_name: str, split: str, batch_size: int, generator: torch.Generator,
+                                device: Optional[torch.device] = None, root=None
+                                ) -> Union[List[Batch], NodeBatches, LinkBatches]:
+    """finetune_data_loaders.py:110-119: dispatch on the domain's task type."""
+    from .models import TASK_TYPES
+    make = {'graph_classification': create_graph_classification_loader, 'node_classification': create_node_classification_loader,
+            'link_prediction': create_link_prediction_loader}[TASK_TYPES[domain_name]]
+    return make(domain_name, split, batch_size, generator, device, root)

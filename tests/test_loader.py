@@ -136,3 +136,81 @@ def test_finetune_loaders_equal_reference_loaders():
         assert len(want) == len(got) == len(mine) and torch.equal(mine.dataset.train_edges, ds.train_edges)
         for (wd, we, wl), (gd, ge, gl) in zip(want, got):
             assert we.dtype == ge.dtype and torch.equal(we, ge) and wl.dtype == gl.dtype and torch.equal(wl, gl)
+
+
+@pytest.mark.skipif(not reference_available(), reason='/root/reference not present')
+def test_on_disk_loader_factories_equal_the_reference(tmp_path, monkeypatch):
+    """The reference's processed-data layout (data.pt / splits.pt / graph_properties.pt, data_setup.py:66-72) written by
+    the REFERENCE's save_processed_data, then read by the reference's loader factories and by gnnb200.loader's factories
+    of the same names: identical batches in identical order (pretrain_data_loaders.py:56-83, finetune_data_loaders.py:68-119)."""
+    load_reference()
+    import src.data.data_setup as ref_setup
+    import src.data.finetune_data_loaders as ref_ft
+    import src.data.pretrain_data_loaders as ref_pt
+    from torch_geometric.data import Data as ShimData
+    for mod in (ref_setup, ref_ft, ref_pt):
+        monkeypatch.setattr(mod, 'PROCESSED_DIR', tmp_path)
+    # two TU-shaped graph domains with properties, one node-classification graph, one link-prediction graph
+    for i, dom in enumerate(['ENZYMES', 'PTC_MR']):
+        graphs = [ShimData(x=g['x'], edge_index=g['edge_index'], y=g['y']) for g in synthetic.tu_like_graphs(dom, 40, seed=5 + i)]
+        perm = torch.randperm(40, generator=torch.Generator().manual_seed(i)).numpy()
+        splits = {'train': perm[:24], 'val': perm[24:32], 'test': perm[32:]}
+        props = torch.randn(40, 12, generator=torch.Generator().manual_seed(20 + i))
+        ref_setup.save_processed_data(dom, graphs, splits, props)
+    d = synthetic.planetoid_like(150, 300, 12, seed=3)
+    y = torch.randint(0, 7, (150,), generator=torch.Generator().manual_seed(0))
+    perm = torch.randperm(150, generator=torch.Generator().manual_seed(1)).numpy()
+    ref_setup.save_processed_data('Cora_NC', [ShimData(x=d['x'], edge_index=d['edge_index'], y=y)],
+                                  {'train': perm[:60], 'val': perm[60:100], 'test': perm[100:]})
+    e = d['edge_index']
+    ref_setup.save_processed_data('Cora_LP', [ShimData(x=d['x'], edge_index=e[:, :300])],
+                                  {'train_pos': e[:, :300], 'val_pos': e[:, 300:340], 'val_neg': e[:, 340:380].flip(0),
+                                   'test_pos': e[:, 380:440], 'test_neg': e[:, 440:500].flip(0)})
+
+    # ---- pre-training: balanced sampler over the train splits (graph_properties attached), validation loader
+    want = ref_pt.create_train_data_loader(['ENZYMES', 'PTC_MR'], torch.Generator().manual_seed(7))
+    got = loader.create_train_data_loader(['ENZYMES', 'PTC_MR'], torch.Generator().manual_seed(7), root=tmp_path)
+    assert len(want) == len(got)
+    for w, g in zip(want, got):
+        assert list(w) == list(g)
+        for dom in w:
+            _same(g[dom], w[dom])
+    want_val = list(ref_pt.create_val_data_loader('PTC_MR', torch.Generator().manual_seed(1)))
+    got_val = loader.create_val_data_loader('PTC_MR', torch.Generator().manual_seed(1), root=tmp_path)
+    assert len(want_val) == len(got_val)
+    for w, g in zip(want_val, got_val):
+        _same(g, w)
+    # ---- fine-tuning: the dispatcher and the three loader kinds
+    for split, bs in (('train', 16), ('test', 5)):
+        w_all = list(ref_ft.create_finetune_data_loader('ENZYMES', split, bs, torch.Generator().manual_seed(2)))
+        g_all = loader.create_finetune_data_loader('ENZYMES', split, bs, torch.Generator().manual_seed(2), root=tmp_path)
+        assert len(w_all) == len(g_all)
+        for w, g in zip(w_all, g_all):
+            _same(g, w, names=('x', 'edge_index', 'batch', 'ptr', 'y'))
+    for bs in (-1, 32):
+        w_all = list(ref_ft.create_finetune_data_loader('Cora_NC', 'val', bs, torch.Generator().manual_seed(2)))
+        g_all = list(loader.create_finetune_data_loader('Cora_NC', 'val', bs, torch.Generator().manual_seed(2), root=tmp_path))
+        assert len(w_all) == len(g_all)
+        for (wd, wi, wl), (gd, gi, gl) in zip(w_all, g_all):
+            assert torch.equal(wd.x, gd.x) and torch.equal(wi, gi) and torch.equal(wl, gl) and wl.dtype == gl.dtype
+    for split in ('train', 'val', 'test'):
+        ref_loader = ref_ft.create_finetune_data_loader('Cora_LP', split, 64, torch.Generator().manual_seed(2))
+        mine = loader.create_finetune_data_loader('Cora_LP', split, 64, torch.Generator().manual_seed(2), root=tmp_path)
+        assert torch.equal(mine.dataset.train_edges, ref_loader.dataset.train_edges)
+        for (wd, we, wl), (gd, ge, gl) in zip(list(ref_loader), list(mine)):
+            assert torch.equal(wd.edge_index, gd.edge_index) and torch.equal(we, ge) and torch.equal(wl, gl)
+
+
+def test_processed_data_round_trip_with_own_classes(tmp_path):
+    """save_processed_data / create_* with the package's own Data class (no PyG, no reference)."""
+    graphs = _graphs('ENZYMES', 10, seed=3)
+    props = torch.stack([g.graph_properties.view(-1) for g in graphs])
+    bare = [Data(x=g.x, edge_index=g.edge_index, y=g.y) for g in graphs]
+    loader.save_processed_data('ENZYMES', bare, {'train': np.arange(6), 'val': np.arange(6, 10)}, props, root=tmp_path)
+    s = loader.create_train_data_loader(['ENZYMES'], torch.Generator().manual_seed(0), root=tmp_path)
+    step = s.draw()['ENZYMES']
+    assert step.num_graphs == loader.BATCH_SIZE and step.graph_properties.numel() == loader.BATCH_SIZE * 12   # PyG cat layout
+    val = loader.create_val_data_loader('ENZYMES', torch.Generator(), root=tmp_path)
+    assert [b.num_graphs for b in val] == [4] and torch.equal(val[0].graph_properties.view(4, 12), props[6:10])
+    ft = loader.create_finetune_data_loader('ENZYMES', 'val', 3, torch.Generator(), root=tmp_path)
+    assert [b.num_graphs for b in ft] == [3, 1]
