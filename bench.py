@@ -116,9 +116,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def make_graph(n, e, f, seed, locality, device):
+def make_graph(n, e, f, seed, locality, device, skew=0.0):
     from gnnb200 import synthetic
-    return synthetic.products_like(n, e, f, seed=seed, locality=locality, device=device)
+    return synthetic.products_like(n, e, f, seed=seed, locality=locality, device=device, skew=skew)
 
 
 def build_model(impl_models, device, f_in, seed=0):
@@ -160,7 +160,7 @@ def run_product(args):
 
     n = max(1024, int(C5_N * args.scale))
     e = max(4096, int(C5_E * args.scale))
-    data = make_graph(n, e, C5_F, 42, args.locality, dev)
+    data = make_graph(n, e, C5_F, 42, args.locality, dev, args.skew)
     x_dev, ei_dev = data['x'], data['edge_index']
 
     if world > 1:
@@ -292,7 +292,7 @@ def run_product(args):
             'data': 'synthetic',
             'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F,
                        'hidden': HIDDEN, 'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
-                       'edge_locality': args.locality, 'gemm_precision': gnn.default_precision(),
+                       'edge_locality': args.locality, 'degree_skew': args.skew, 'gemm_precision': gnn.default_precision(),
                        'l2_policy': 'inputs_larger_than_L2 (2.5 GB activations per layer vs 126 MB L2)',
                        'parallelism': 'single' if world == 1 else f'node_partition{world}+' + (
                            {'sparse': 'halo_alltoall_sparse', 'peer': 'halo_read_in_gather_over_nvlink_peer_memory',
@@ -569,7 +569,7 @@ def cpu_run(args, steps, warmup):
     from oracle import modules as orc
     torch.set_num_threads(os.cpu_count() or 1)
     n, e = cpu_sample_sizes(args)
-    data = make_graph(n, e, C5_F, 42, args.locality, 'cpu')
+    data = make_graph(n, e, C5_F, 42, args.locality, 'cpu', args.skew)
     model = build_model(orc, torch.device('cpu'), C5_F)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
     times = []
@@ -619,6 +619,8 @@ def main():
     ap.add_argument('--impl', default='gnnb200', choices=['gnnb200', 'reference'])
     ap.add_argument('--scale', type=float, default=1.0, help='fraction of the C5 graph (debug only; 1.0 = BASELINE config)')
     ap.add_argument('--locality', type=float, default=0.0, help='fraction of intra-block edges (0 = uniform random)')
+    ap.add_argument('--skew', type=float, default=0.0,
+                    help='> 1: power-law endpoints (1.8 ~ ogbn-products: largest hub 2.8e-4 of all edges); 0 = uniform (default)')
     ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3'])
     ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'auto', 'peer', 'peercopy'],
                     help='N > 1: rows exchanged per layer (default dense = all-gather; see gnnb200/partition.py)')

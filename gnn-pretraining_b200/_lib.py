@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libgnnb200.so')
 
 OK, EINVAL, ERANGE, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
 AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
-AGG_ACCUMULATE = 8
+AGG_ACCUMULATE, AGG_SKIP_LONG, AGG_LONG_ROW = 8, 16, 1024
 POOL_SUM, POOL_MEAN, POOL_MAX = 0, 1, 2
 GEMM_F32, GEMM_TF32, GEMM_AUTO, GEMM_TF32X3, GEMM_AUTO_X3 = 0, 1, 2, 3, 4
 EPI_NONE, EPI_RELU = 0, 1
@@ -43,6 +43,7 @@ SIGNATURES = {
     'gnnb200_segment_ptr_i64': [P, I64, I64, P, P],
     'gnnb200_coalesce_i64': [P, I64, I64, P, P, P, SZP, P],
     'gnnb200_aggregate_f32': [P, I64, P, P, I64, I64, c_int, P, I64, P, P, P, I64, P],
+    'gnnb200_aggregate_long_rows_f32': [P, I64, P, P, P, I64, I64, c_int, P, I64, P, P, I64, P],
     'gnnb200_dot_f32': [P, P, I64, P, P, SZP, P],
     'gnnb200_segment_pool_fwd_f32': [P, I64, P, I64, I64, I64, c_int, P, I64, P, SZP, P],
     'gnnb200_segment_pool_bwd_f32': [P, I64, P, I64, P, I64, P, I64, I64, I64, c_int, P, I64, P],

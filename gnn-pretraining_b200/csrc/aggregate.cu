@@ -9,7 +9,9 @@
 
 namespace gnnb200 {
 
-template <int G, int V, int MODE, int U = 4, int MINB = 1>
+// SKIP (SUM mode, opt-in through GNNB200_AGG_SKIP_LONG): rows with more than GNNB200_AGG_LONG_ROW neighbours are left to
+// aggregate_long_rows_kernel below, so one hub node cannot hold the whole launch hostage to a single warp's serial walk.
+template <int G, int V, int MODE, int U = 4, int MINB = 1, bool SKIP = false>
 __global__ void __launch_bounds__(256, MINB)
 aggregate_vec_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
                      const int32_t* __restrict__ col, int64_t num_rows, int feat,
@@ -23,6 +25,7 @@ aggregate_vec_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __
   if (group >= num_rows) return;
   const int64_t row = group;
   const int beg = rowptr[row], end = rowptr[row + 1];
+  if (SKIP && end - beg > GNNB200_AGG_LONG_ROW) return;
   const int nvec = feat >> 2;                    // float4 per row
 
   float4 acc[V];
@@ -117,10 +120,74 @@ aggregate_scalar_kernel(const float* __restrict__ x, int64_t ldx, const int32_t*
   }
 }
 
+// One CTA per long row (a hub of a power-law graph): its 8 warps walk 8 contiguous slices of the neighbour list, each in
+// edge order with the same streaming loads as above, and the 8 partial rows are added in warp order through shared
+// memory: deterministic (same inputs -> same bits), but a different association than the single sequential sum, so these
+// rows agree with the CPU order to fp32 rounding (1e-5 class) instead of bit for bit.
+template <int V>
+__global__ void __launch_bounds__(256)
+aggregate_long_rows_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
+                           const int32_t* __restrict__ col, const int64_t* __restrict__ rows, int feat,
+                           const float* __restrict__ self_x, int64_t lds, const float* __restrict__ eps_ptr,
+                           float* __restrict__ out, int64_t ldo, int accumulate) {
+  extern __shared__ float4 part[];               // [8 warps][nvec]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = rows[blockIdx.x];
+  const int beg = rowptr[row], end = rowptr[row + 1];
+  const int nvec = feat >> 2;
+  const int per = (((end - beg + 7) >> 3) + 31) & ~31;          // neighbours per warp, a multiple of 32
+  const int w_beg = min(end, beg + warp * per), w_end = min(end, w_beg + per);
+  constexpr int U = 2;
+
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = w_beg; base < w_end; base += 32) {
+    const int my_col = (base + lane < w_end) ? col[base + lane] : 0;
+    const int cnt = min(32, w_end - base);
+    for (int j = 0; j < cnt; j += U) {
+      float4 nb[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = min(j + u, cnt - 1);
+        const int c = __shfl_sync(0xffffffffu, my_col, jj);
+        const float4* src = reinterpret_cast<const float4*>(x + (int64_t)c * ldx);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int k = lane + v * 32;
+          if (j + u < cnt && k < nvec) nb[u][v] = ldg_stream(src + k);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j + u < cnt) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (lane + v * 32 < nvec) acc[v] = f4_add(acc[v], nb[u][v]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int k = lane + v * 32;
+    if (k < nvec) part[warp * nvec + k] = acc[v];
+  }
+  __syncthreads();
+  const float scale = (self_x != nullptr) ? __fadd_rn(1.0f, eps_ptr ? *eps_ptr : 0.f) : 0.f;
+  for (int k = threadIdx.x; k < nvec; k += 256) {
+    float4 r = accumulate ? *reinterpret_cast<const float4*>(out + row * ldo + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r = f4_add(r, part[w * nvec + k]);
+    if (self_x != nullptr) r = f4_add(r, f4_scale(scale, *reinterpret_cast<const float4*>(self_x + row * lds + 4 * k)));
+    *reinterpret_cast<float4*>(out + row * ldo + 4 * k) = r;
+  }
+}
+
 template <int G, int V>
 static int launch_vec(int mode, int accumulate, const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
                       int64_t num_rows, int feat, const float* self_x, int64_t lds, const float* eps,
-                      const float* dinv, float* out, int64_t ldo, cudaStream_t stream) {
+                      const float* dinv, float* out, int64_t ldo, cudaStream_t stream, bool skip_long = false) {
   const int block = 256;
   const int64_t threads = num_rows * G;
   const unsigned grid = (unsigned)((threads + block - 1) / block);
@@ -131,7 +198,10 @@ static int launch_vec(int mode, int accumulate, const float* x, int64_t ldx, con
   constexpr int MINB = (V <= 2) ? 6 : ((V == 4) ? 3 : 2);
   switch (mode) {
     case GNNB200_AGG_SUM:
-      aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
+      if (skip_long)
+        aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB, true><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
+      else
+        aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
       break;
     case GNNB200_AGG_MEAN:
       aggregate_vec_kernel<G, V, GNNB200_AGG_MEAN, U, MINB><<<grid, block, 0, stream>>>(x, ldx, rowptr, col, num_rows, feat, self_x, lds, eps, dinv, out, ldo, accumulate);
@@ -154,9 +224,10 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
                                      gnnb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int accumulate = (mode & GNNB200_AGG_ACCUMULATE) ? 1 : 0;
-  mode &= ~GNNB200_AGG_ACCUMULATE;
+  const bool skip_long = (mode & GNNB200_AGG_SKIP_LONG) != 0;
+  mode &= ~(GNNB200_AGG_ACCUMULATE | GNNB200_AGG_SKIP_LONG);
   if (num_rows < 0 || feat < 0 || mode < 0 || mode > 2) return GNNB200_EINVAL;
-  if (accumulate && mode != GNNB200_AGG_SUM) return GNNB200_EINVAL;
+  if ((accumulate || skip_long) && mode != GNNB200_AGG_SUM) return GNNB200_EINVAL;
   if (num_rows == 0 || feat == 0) return GNNB200_OK;
   if (!x || !rowptr || !out) return GNNB200_EINVAL;
   if (mode == GNNB200_AGG_GCN && (!dinv || !self_x)) return GNNB200_EINVAL;
@@ -165,7 +236,8 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
                       ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)self_x % 16 == 0) &&
                       feat <= 1024;
   const int f = (int)feat;
-#define GNNB200_AGG_ARGS mode, accumulate, x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, stream
+#define GNNB200_AGG_ARGS mode, accumulate, x, ldx, rowptr, col, num_rows, f, self_x, lds, eps, dinv, out, ldo, stream, skip_long
+  if (skip_long && !vec_ok) return GNNB200_EUNSUPPORTED;   // the long-row kernel exists for the 128-bit layouts only
   if (vec_ok) {
     const int nvec = f / 4;
     if (nvec <= 4) return launch_vec<4, 1>(GNNB200_AGG_ARGS);
@@ -194,6 +266,32 @@ extern "C" int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t*
   return GNNB200_OK;
 }
 
+extern "C" int gnnb200_aggregate_long_rows_f32(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
+                                               const int64_t* rows, int64_t num_long_rows, int64_t feat, int mode,
+                                               const float* self_x, int64_t lds, const float* eps, float* out,
+                                               int64_t ldo, gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int accumulate = (mode & GNNB200_AGG_ACCUMULATE) ? 1 : 0;
+  mode &= ~(GNNB200_AGG_ACCUMULATE | GNNB200_AGG_SKIP_LONG);
+  if (num_long_rows < 0 || feat < 0 || mode != GNNB200_AGG_SUM) return GNNB200_EINVAL;
+  if (num_long_rows == 0 || feat == 0) return GNNB200_OK;
+  if (!x || !rowptr || !col || !rows || !out) return GNNB200_EINVAL;
+  if (num_long_rows >= (int64_t)INT32_MAX) return GNNB200_ERANGE;
+  if (feat % 4 != 0 || feat > 1024 || ldx % 4 != 0 || ldo % 4 != 0 || (self_x && lds % 4 != 0) || (uintptr_t)x % 16 != 0 ||
+      (uintptr_t)out % 16 != 0 || (uintptr_t)self_x % 16 != 0)
+    return GNNB200_EUNSUPPORTED;
+  const int f = (int)feat, nvec = f / 4;
+  const size_t smem = (size_t)8 * nvec * sizeof(float4);
+  const unsigned grid = (unsigned)num_long_rows;
+#define GNNB200_LONG_ARGS x, ldx, rowptr, col, rows, f, self_x, lds, eps, out, ldo, accumulate
+  if (nvec <= 32) aggregate_long_rows_kernel<1><<<grid, 256, smem, stream>>>(GNNB200_LONG_ARGS);
+  else if (nvec <= 64) aggregate_long_rows_kernel<2><<<grid, 256, smem, stream>>>(GNNB200_LONG_ARGS);
+  else if (nvec <= 128) aggregate_long_rows_kernel<4><<<grid, 256, smem, stream>>>(GNNB200_LONG_ARGS);
+  else aggregate_long_rows_kernel<8><<<grid, 256, smem, stream>>>(GNNB200_LONG_ARGS);
+#undef GNNB200_LONG_ARGS
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
 
 // Development-only tuning hook (not part of include/gnnb200.h): SUM mode, F = 256, 16-byte aligned.
 extern "C" int gnnb200_dev_aggregate_variant(const float* x, const int32_t* rowptr, const int32_t* col, int64_t num_rows,

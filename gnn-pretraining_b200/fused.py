@@ -18,6 +18,7 @@ import torch
 from torch import Tensor
 
 from . import _lib as L
+from . import graph as graph_mod
 from . import ops
 from .graph import Graph
 
@@ -28,10 +29,13 @@ from .graph import Graph
 NATIVE_LAYER = os.environ.get('GNNB200_NATIVE_LAYER', '0') == '1'
 
 
-def _native_usable(h: Tensor, tensors, bn1, bn2) -> bool:
+def _native_usable(h: Tensor, tensors, bn1, bn2, graph, need_t: bool) -> bool:
     """Layouts the composite assumes: dense parameters, fp32 rows, standard BatchNorm buffers, no per-launch timing."""
     if ops.AGG_TIMER is not None or h.dtype != torch.float32 or bn1.running_mean is None or bn2.running_mean is None:
         return False
+    if graph_mod.LONG_ROWS and (getattr(graph, 'long_rows', None) is not None or
+                                (need_t and getattr(graph, 'long_rows_t', None) is not None)):
+        return False                  # hub rows take the block-per-row kernel: Python path
     return all(t is None or t.is_contiguous() for t in tensors)
 
 
@@ -103,13 +107,14 @@ class GINLayerFn(torch.autograd.Function):
                 g2: Tensor, be2: Tensor, graph: Graph, bn1, bn2, training: bool, drop_p: float, seed: int, precision: int):
         h = ops._rowmajor(h)
         ctx.graph, ctx.cfg = graph, (training, drop_p, seed, precision)
-        ctx.native = NATIVE_LAYER and _native_usable(h, (eps, w1, b1, g1, be1, w2, b2, g2, be2), bn1, bn2)
+        ctx.native = NATIVE_LAYER and _native_usable(h, (eps, w1, b1, g1, be1, w2, b2, g2, be2), bn1, bn2, graph,
+                                                     training and h.requires_grad)
         if ctx.native:
             out, saved = _native_forward(h, eps, w1, b1, g1, be1, w2, b2, g2, be2, graph, bn1, bn2, training, drop_p, seed,
                                          precision)
             ctx.save_for_backward(h, eps, w1, g1, be1, w2, g2, be2, *saved)
             return out
-        z = ops._aggregate_raw(h, graph.rowptr, graph.col, L.AGG_SUM, h, eps, None)
+        z = ops._aggregate_raw(h, graph.rowptr, graph.col, L.AGG_SUM, h, eps, None, long_rows=getattr(graph, 'long_rows', None))
         a1 = ops._gemm_raw(z, False, w1, True, b1, False, precision)
         mean1, invstd1 = _stats(bn1, a1, training)
         r1 = ops.bn_act.fn(a1, mean1, invstd1, g1, be1, True, 0.0, 0, training, 0)
@@ -143,7 +148,8 @@ class GINLayerFn(torch.autograd.Function):
         dh = None
         if ctx.needs_input_grad[0]:
             rowptr_t, col_t = graph.rowptr_t, graph.col_t
-            dh = ops._aggregate_raw(dz, rowptr_t, col_t, L.AGG_SUM, dz, eps, None, out=ds)   # ds is dead: reuse it
+            dh = ops._aggregate_raw(dz, rowptr_t, col_t, L.AGG_SUM, dz, eps, None, out=ds,    # ds is dead: reuse it
+                                    long_rows=getattr(graph, 'long_rows_t', None))
         return (dh, deps, dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None)
 
 

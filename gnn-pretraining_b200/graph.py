@@ -1,14 +1,31 @@
 """Sorted-CSR view of an ``edge_index`` tensor, built on the device once and reused by every layer
 and every pass that sees the same tensor (the reference rebuilds nothing because it has no CSR;
 SURVEY.md §8a row a4)."""
+import os
 from typing import Optional
 
 import torch
 from torch import Tensor
 
+from . import _lib as L
 from . import ops
 
 _ATTR = '_gnnb200_graph'
+
+# GNNB200_LONG_ROWS=1: graphs with at least LONG_ROW_MIN_EDGES edges are checked for rows with more than L.AGG_LONG_ROW
+# neighbours (one nonzero() = one device sync per CSR build); those rows then take the block-per-row kernel instead of one
+# warp's serial walk (a 17,000-neighbour hub of a products-like graph would otherwise run ~8 ms on its own).  Opt-in until
+# measured; batches of small graphs never pay the sync.
+LONG_ROWS = os.environ.get('GNNB200_LONG_ROWS', '0') == '1'
+LONG_ROW_MIN_EDGES = 1 << 16
+
+
+def long_rows_of(rowptr: Tensor, num_edges: int) -> Optional[Tensor]:
+    """int64 ids of the rows longer than L.AGG_LONG_ROW, or None (none, small graph, or the feature is off)."""
+    if not LONG_ROWS or num_edges < LONG_ROW_MIN_EDGES:
+        return None
+    ids = torch.nonzero((rowptr[1:] - rowptr[:-1]) > L.AGG_LONG_ROW).view(-1)
+    return ids if ids.numel() else None
 
 
 class Graph:
@@ -21,13 +38,14 @@ class Graph:
         self.num_nodes = int(num_nodes)
         self.num_edges = int(edge_index.size(1))
         self.rowptr, self.col, _ = ops.csr_build(edge_index, self.num_nodes, False)   # the edge permutation is not kept
+        self.long_rows = long_rows_of(self.rowptr, self.num_edges)
         self._t = None
         self._version = edge_index._version
 
     def transposed(self):
         if self._t is None:
             rowptr_t, col_t, _ = ops.csr_build(self.edge_index, self.num_nodes, True)
-            self._t = (rowptr_t, col_t)
+            self._t = (rowptr_t, col_t, long_rows_of(rowptr_t, self.num_edges))
         return self._t
 
     @property
@@ -37,6 +55,10 @@ class Graph:
     @property
     def col_t(self) -> Tensor:
         return self.transposed()[1]
+
+    @property
+    def long_rows_t(self) -> Optional[Tensor]:
+        return self.transposed()[2]
 
     def in_degree(self) -> Tensor:
         return (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)

@@ -72,7 +72,7 @@ def _ld(t: Tensor) -> int:
 # Own-kernel launches per entry-point call (library kernels such as CUB's sort are not counted).
 KERNELS_PER_CALL = {
     'gnnb200_csr_build_i64': 2, 'gnnb200_segment_ptr_i64': 1, 'gnnb200_coalesce_i64': 3,
-    'gnnb200_aggregate_f32': 1, 'gnnb200_dot_f32': 2, 'gnnb200_segment_pool_fwd_f32': 1,
+    'gnnb200_aggregate_f32': 1, 'gnnb200_aggregate_long_rows_f32': 1, 'gnnb200_dot_f32': 2, 'gnnb200_segment_pool_fwd_f32': 1,
     'gnnb200_segment_pool_bwd_f32': 1, 'gnnb200_rows_gather_f32': 1, 'gnnb200_rows_scatter_f32': 1,
     'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_colstats_f32': 2,
     'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
@@ -269,8 +269,11 @@ def _(edge_index, num_nodes):
 # aggregation
 # ---------------------------------------------------------------------------------------------
 def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Optional[Tensor],
-                   eps: Optional[Tensor], dinv: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
-    """out given => accumulate into it (GNNB200_AGG_ACCUMULATE): a later pass of a chunked aggregation."""
+                   eps: Optional[Tensor], dinv: Optional[Tensor], out: Optional[Tensor] = None,
+                   long_rows: Optional[Tensor] = None) -> Tensor:
+    """out given => accumulate into it (GNNB200_AGG_ACCUMULATE): a later pass of a chunked aggregation.
+    long_rows (int64 ids of the rows with more than L.AGG_LONG_ROW neighbours, SUM mode): the main launch skips them and a
+    block-per-row kernel covers them (gnnb200_aggregate_long_rows_f32)."""
     _need_cuda(x, rowptr, col, self_x, eps, dinv)
     x = _rowmajor(x)
     n_rows = rowptr.numel() - 1
@@ -280,6 +283,11 @@ def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Op
         mode |= L.AGG_ACCUMULATE
     if self_x is not None:
         self_x = _rowmajor(self_x)
+    split_long = (long_rows is not None and (mode & 7) == L.AGG_SUM and x.size(1) % 4 == 0 and x.size(1) <= 1024
+                  and _ld(x) % 4 == 0 and x.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and _ld(out) % 4 == 0
+                  and (self_x is None or (_ld(self_x) % 4 == 0 and self_x.data_ptr() % 16 == 0)))
+    if split_long:
+        mode |= L.AGG_SKIP_LONG
     timer = AGG_TIMER
     if timer is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -288,6 +296,11 @@ def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Op
         _ptr(x), _ld(x), _ptr(rowptr), _ptr(col), n_rows, x.size(1), mode,
         _ptr(self_x), _ld(self_x) if self_x is not None else 0, _ptr(eps), _ptr(dinv),
         _ptr(out), _ld(out), _stream(x)), 'aggregate')
+    if split_long:
+        L.check(_invoke('gnnb200_aggregate_long_rows_f32', _ptr(x), _ld(x), _ptr(rowptr), _ptr(col), _ptr(long_rows),
+                        long_rows.numel(), x.size(1), mode & ~L.AGG_SKIP_LONG, _ptr(self_x),
+                        _ld(self_x) if self_x is not None else 0, _ptr(eps), _ptr(out), _ld(out), _stream(x)),
+                'aggregate (long rows)')
     if timer is not None:
         ev[1].record()
         timer.append(ev)

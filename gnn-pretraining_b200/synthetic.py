@@ -92,16 +92,27 @@ def tu_like_graphs(domain: str, num_graphs: int, seed: int = 42, num_classes: in
 
 
 def products_like(num_nodes: int = C5_NODES, num_edges: int = C5_EDGES, feats: int = C5_FEATS,
-                  seed: int = 42, locality: float = 0.0, blocks: int = 64, device='cpu'
+                  seed: int = 42, locality: float = 0.0, blocks: int = 64, device='cpu', skew: float = 0.0
                   ) -> Dict[str, torch.Tensor]:
     """C5: one large directed multigraph in COO, random column order.  `locality` is the
     fraction of edges whose source is drawn from the destination's block of N/blocks nodes
     (0.0 = uniform random = worst-case gather locality; 0.9 mimics community structure).
-    Duplicates/self loops are kept: GINConv treats them as ordinary edges (App. A.1)."""
+    Duplicates/self loops are kept: GINConv treats them as ordinary edges (App. A.1).
+    `skew` > 1 draws both endpoints from a power law instead (node rank r with probability ~ r^(1/skew - 1), ranks
+    scattered over the id space): skew = 1.8 gives the largest hub ~2.8e-4 of all edges, ogbn-products' ratio (17 k of
+    62 M) — SURVEY §8d input 5(ii), "degree-skewed".  skew = 0 (default) consumes exactly the stream it always did."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    dst = torch.randint(0, num_nodes, (num_edges,), generator=g, device=device)
-    src = torch.randint(0, num_nodes, (num_edges,), generator=g, device=device)
+    if skew > 1.0:
+        spread = torch.randperm(num_nodes, generator=g, device=device)
+
+        def draw():
+            rank = (torch.rand(num_edges, generator=g, device=device, dtype=torch.float64) ** skew * num_nodes).long()
+            return spread[rank.clamp_(max=num_nodes - 1)]
+        dst, src = draw(), draw()
+    else:
+        dst = torch.randint(0, num_nodes, (num_edges,), generator=g, device=device)
+        src = torch.randint(0, num_nodes, (num_edges,), generator=g, device=device)
     if locality > 0.0:
         bs = (num_nodes + blocks - 1) // blocks
         local = torch.rand(num_edges, generator=g, device=device) < locality

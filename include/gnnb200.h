@@ -76,10 +76,21 @@ int gnnb200_coalesce_i64(const int64_t* edge_index, int64_t num_edges, int64_t n
 #define GNNB200_AGG_MEAN 1
 #define GNNB200_AGG_GCN 2
 #define GNNB200_AGG_ACCUMULATE 8 /* OR into SUM: start each row's sum from the value already in out (chunked halo passes) */
+#define GNNB200_AGG_SKIP_LONG 16 /* OR into SUM: leave rows with more than GNNB200_AGG_LONG_ROW neighbours untouched; the caller covers
+                                    them with gnnb200_aggregate_long_rows_f32 (128-bit layouts only, else GNNB200_EUNSUPPORTED) */
+#define GNNB200_AGG_LONG_ROW 1024
 int gnnb200_aggregate_f32(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
                           int64_t num_rows, int64_t feat, int mode, const float* self_x, int64_t lds,
                           const float* eps, const float* dinv, float* out, int64_t ldo,
                           gnnb200_stream_t stream);
+
+/* The rows listed in `rows` (int64 [num_long_rows]; the hubs of a skewed degree distribution) of the same aggregation, one
+ * thread block per row: 8 warps sum 8 contiguous slices of the neighbour list in edge order and the partial rows are added
+ * in slice order — deterministic, equal to the sequential sum up to fp32 re-association.  mode: SUM [| ACCUMULATE]. */
+int gnnb200_aggregate_long_rows_f32(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
+                                    const int64_t* rows, int64_t num_long_rows, int64_t feat, int mode,
+                                    const float* self_x, int64_t lds, const float* eps, float* out, int64_t ldo,
+                                    gnnb200_stream_t stream);
 
 /* Deterministic dot product sum(a*b) over n elements -> *out (device).  d(eps) of GINConv. */
 int gnnb200_dot_f32(const float* a, const float* b, int64_t n, float* out, void* workspace,

@@ -24,4 +24,6 @@ GNNB200_NATIVE_LAYER=1       run bench_secondary_native   $B
 run bench_c4_n1              python bench.py --workload c4 --steps 20 --warmup 5
 GNNB200_NATIVE_LAYER=1       run bench_c4_n1_native       python bench.py --workload c4 --steps 20 --warmup 5
 run bench_c5_locality09      $B --no-secondary --locality 0.9
+run bench_c5_skew18          $B --no-secondary --locality 0.9 --skew 1.8
+GNNB200_LONG_ROWS=1          run bench_c5_skew18_longrows $B --no-secondary --locality 0.9 --skew 1.8
 cat gpurun_out/r02_call1_status.txt

@@ -110,6 +110,12 @@ BAD = [
     ('gnnb200_pcgrad_f32', (D, D, -1, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, None, 2, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, D, 70000, 10, D, 2, D, D, D, D, D, D, None), L.ERANGE),                       # > 65535 tasks
+    # ---- long rows ----
+    ('gnnb200_aggregate_long_rows_f32', (D, 256, D, D, None, 3, 256, 0, None, 0, None, D, 256, None), L.EINVAL),      # no row list
+    ('gnnb200_aggregate_long_rows_f32', (D, 256, D, D, D, 3, 256, 1, None, 0, None, D, 256, None), L.EINVAL),         # MEAN
+    ('gnnb200_aggregate_long_rows_f32', (D, 254, D, D, D, 3, 254, 0, None, 0, None, D, 256, None), L.EUNSUPPORTED),   # not 128-bit
+    ('gnnb200_aggregate_f32', (D, 254, D, D, 4, 254, 16, None, 0, None, None, D, 256, None), L.EUNSUPPORTED),          # SKIP_LONG needs it too
+    ('gnnb200_aggregate_f32', (D, 256, D, D, 4, 256, 17, None, 0, None, None, D, 256, None), L.EINVAL),               # SKIP_LONG with MEAN
     # ---- peer-memory aggregation ----
     ('gnnb200_aggregate_peer_f32', (None, 2, 256, D, D, 4, 256, None, 0, None, D, 256, None), L.EINVAL),     # no pointer table
     ('gnnb200_aggregate_peer_f32', (D, 17, 256, D, D, 4, 256, None, 0, None, D, 256, None), L.EINVAL),       # > GNNB200_MAX_PEERS

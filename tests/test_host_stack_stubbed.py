@@ -172,3 +172,30 @@ def test_bench_secondary_workloads_run_through_the_host_stack(stubbed):
     assert out['c2_shape']['graphs'] == 128 and out['c3_shape']['tasks'] == bench.S4_TASKS
     assert all(out[k] > 0 for k in ('c1_edges_per_s', 'c2_finetune_steps_per_s', 'c3_s4_pretrain_steps_per_s'))
     assert stubbed['gnnb200_pcgrad_f32'] >= 2 and stubbed['gnnb200_ntxent_fwd_f32'] + stubbed.get('gnnb200_ntxent_sim_fwd_f32', 0) > 0
+
+
+def test_long_rows_plumbing(stubbed, monkeypatch):
+    """GNNB200_LONG_ROWS: the CSR build lists the rows above the threshold (host check of the index arithmetic) and the
+    aggregation issues the skip-flagged launch followed by the block-per-row launch over exactly those rows."""
+    from gnnb200 import _lib as L, graph as graph_mod
+    rowptr = torch.tensor([0, 3, 3 + 2000, 3 + 2000 + 1024, 3 + 2000 + 1024 + 1025], dtype=torch.int32)
+    assert graph_mod.long_rows_of(rowptr, 10 ** 6) is None                            # feature off by default
+    monkeypatch.setattr(graph_mod, 'LONG_ROWS', True)
+    assert graph_mod.long_rows_of(rowptr, 10) is None                                 # small graphs never pay the sync
+    ids = graph_mod.long_rows_of(rowptr, 10 ** 6)
+    assert ids.tolist() == [1, 3]                                                     # 1024 neighbours is not "long"
+    seen = []
+    monkeypatch.setattr(ops, '_invoke', lambda name, *a: seen.append((name, a)) or 0)
+    x = torch.zeros(4, 256)
+    col = torch.zeros(int(rowptr[-1]), dtype=torch.int32)
+    ops._aggregate_raw(x, rowptr, col, L.AGG_SUM, x, torch.zeros(1), None, long_rows=ids)
+    (n1, a1), (n2, a2) = seen
+    assert n1 == 'gnnb200_aggregate_f32' and a1[6] == L.AGG_SUM | L.AGG_SKIP_LONG
+    assert n2 == 'gnnb200_aggregate_long_rows_f32' and a2[4] == ids.data_ptr() and a2[5] == 2 and a2[7] == L.AGG_SUM
+    assert a2[11] == a1[11]                                                           # same output buffer
+    seen.clear()
+    ops._aggregate_raw(x, rowptr, col, L.AGG_SUM, x, torch.zeros(1), None, out=torch.zeros(4, 256), long_rows=ids)
+    assert seen[0][1][6] == L.AGG_SUM | L.AGG_ACCUMULATE | L.AGG_SKIP_LONG and seen[1][1][7] == L.AGG_SUM | L.AGG_ACCUMULATE
+    seen.clear()
+    ops._aggregate_raw(torch.zeros(4, 255), rowptr, col, L.AGG_SUM, None, None, None, long_rows=ids)    # no 128-bit layout
+    assert [n for n, _ in seen] == ['gnnb200_aggregate_f32'] and seen[0][1][6] == L.AGG_SUM
