@@ -628,13 +628,14 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
     ap.add_argument('--no-secondary', action='store_true', help='skip the small-graph configs (C1 backbone, C2 fine-tune step, C3 s4 step)')
+    ap.add_argument('--secondary-steps', type=int, default=40, dest='secondary_steps', help='timed steps per small-graph config with --only-secondary')
     ap.add_argument('--only-secondary', action='store_true', help='time only the small-graph configs and print them')
     ap.add_argument('--workload', default='c5', choices=['c5', 'c4'], help='c5 = headline (default); c4 = data-parallel s5 pre-training step')
     args = ap.parse_args()
     if args.only_secondary:
         import gnnb200  # noqa: F401
         dev = torch.device('cuda', 0)
-        sec = small_graph_steps('gnnb200', dev, steps=40, warmup=6)
+        sec = small_graph_steps('gnnb200', dev, steps=args.secondary_steps, warmup=min(6, args.secondary_steps))
         if not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             sec['cpu_oracle'] = small_graph_steps('oracle', torch.device('cpu'), steps=4, warmup=1)

@@ -9,4 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 for k in aggregate_vec gemm_tf32 bn_act_bwd_apply bn_act_fwd colstats_partial; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -o gpurun_out/r02_$k -f $CMD > gpurun_out/r02_ncu_$k.log 2>&1
 done
+# small-graph steps: sum of kernel times vs wall time per step tells whether C2/C3 are host- or device-bound
+python bench.py --only-secondary --no-cpu-baseline > gpurun_out/r02_secondary_plain.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file gpurun_out/r02_launches_secondary.csv python bench.py --only-secondary --no-cpu-baseline --secondary-steps 2 > gpurun_out/r02_ncu_secondary.log 2>&1
 ls -la gpurun_out | tail -20
