@@ -48,6 +48,22 @@ def test_gin_aggregate_forward_bit_exact(n, e, f):
     assert torch.equal(got.cpu(), want)
 
 
+@pytest.mark.parametrize('n,e,f', [(10, 0, 256), (64, 300, 256), (2708, 10556, 256), (300, 2000, 100), (50, 5000, 256)])
+def test_csr_and_aggregation_against_the_c_oracle(n, e, f):
+    """The same inputs as above against the SECOND oracle (plain C, oracle/c/oracle_c.c): CSR / CSC arrays and the forward and
+    transposed sums, bit for bit."""
+    from oracle import c_oracle
+    ei = _graph(n, e, n + e + f)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    eps = torch.tensor([0.37])
+    gr = Graph(ei.to(DEV), n)
+    for by_src, (rowptr, col) in ((False, (gr.rowptr, gr.col)), (True, (gr.rowptr_t, gr.col_t))):
+        want_ptr, want_col, _ = c_oracle.csr_build(ei, n, by_src)
+        assert torch.equal(rowptr.cpu(), want_ptr) and torch.equal(col.cpu(), want_col)
+        got = ops._aggregate_raw(x.to(DEV), rowptr, col, L.AGG_SUM, x.to(DEV), eps.to(DEV), None)
+        assert torch.equal(got.cpu(), c_oracle.gin_aggregate(x, ei, 0.37, transposed=by_src))
+
+
 @pytest.mark.parametrize('n,e,f', [(64, 300, 256), (2708, 10556, 256), (300, 2000, 100), (200, 1500, 7)])
 def test_gin_aggregate_backward(n, e, f):
     ei = _graph(n, e, 3 * n + e)

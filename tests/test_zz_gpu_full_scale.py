@@ -95,3 +95,25 @@ def test_batchnorm_full_c5_rows_against_torch(cols):
     assert float(gdiff[away].max()) < 5e-5
     assert rel(mine.weight.grad, ref.weight.grad) < 5e-3 and rel(mine.bias.grad, ref.bias.grad) < 5e-3
     assert rel(mine.running_mean, ref.running_mean) < 1e-5 and rel(mine.running_var, ref.running_var) < 1e-5
+
+
+@pytest.mark.gpu
+@_unverified
+def test_aggregation_full_c5_every_row_against_the_c_oracle():
+    """Not a sample: the WHOLE [2,449,029 x 256] output of the forward aggregation at BASELINE config 5's size, bit for bit
+    against the plain-C edge-order loop (oracle/c/oracle_c.c, one host thread, ~1 min), and the transposed pass likewise."""
+    from gnnb200 import _lib as L, ops
+    from gnnb200.graph import Graph
+    from oracle import c_oracle
+    dev = torch.device('cuda')
+    d = synthetic.products_like(synthetic.C5_NODES, synthetic.C5_EDGES, 4, seed=11)
+    ei = d['edge_index']
+    x = torch.randn(synthetic.C5_NODES, 256, generator=torch.Generator().manual_seed(12))
+    eps = torch.tensor([0.25])
+    g = Graph(ei.to(dev), synthetic.C5_NODES)
+    xd, ed = x.to(dev), eps.to(dev)
+    got = ops._aggregate_raw(xd, g.rowptr, g.col, L.AGG_SUM, xd, ed, None).cpu()
+    assert torch.equal(got, c_oracle.gin_aggregate(x, ei, 0.25))
+    del got
+    got_t = ops._aggregate_raw(xd, g.rowptr_t, g.col_t, L.AGG_SUM, xd, ed, None).cpu()
+    assert torch.equal(got_t, c_oracle.gin_aggregate(x, ei, 0.25, transposed=True))
