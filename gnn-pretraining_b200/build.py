@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}:\n{out.decode()}')
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', LIB, *objs, '-cudart', 'static']
+    cmd = [nvcc, '-shared', '-Wno-deprecated-gpu-targets', '-o', LIB, *objs, '-cudart', 'static']
     subprocess.run(cmd, check=True)
     return LIB
 
