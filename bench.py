@@ -604,7 +604,7 @@ def run_reference(args):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F, 'hidden': HIDDEN,
                    'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW on host cores (oracle port of the reference)',
-                   'edge_locality': args.locality},
+                   'edge_locality': args.locality, 'degree_skew': args.skew},
         'cpu_baseline': base,
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
