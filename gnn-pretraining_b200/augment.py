@@ -28,75 +28,76 @@ NODE_DROP_MIN_NUM_NODES = 3
 NODE_DROP_RATE = 0.2
 
 
-class _ViewPlan:
-    """Host-side description of one augmented view of the whole batch."""
+class _ViewDraws:
+    """What the random stream decided for one view of the whole batch (the draws are per graph and sequential, because they
+    must consume the reference's CPU generator in its order; everything derived from them is assembled batch-wide)."""
 
-    def __init__(self):
-        self.total = 0                            # nodes of the view batch so far
-        self.node_ids: List[np.ndarray] = []      # global ids of kept nodes, per graph (ascending)
-        self.edges: List[np.ndarray] = []         # [2, e'] relabelled + offset into the view batch, per graph
-        self.sizes: List[int] = []
-        self.mask_rows: List[np.ndarray] = []     # flat indices into x_view.view(-1) to zero
-        self.kept_local: List[np.ndarray] = []
-
-    def add(self, start: int, kept: np.ndarray, edges: np.ndarray, feat_cols, num_feats: int):
-        offset = self.total
-        self.total += int(kept.size)
-        self.node_ids.append(kept + start)
-        self.edges.append(edges + offset)
-        if feat_cols is not None and kept.size:
-            rows = np.arange(offset, offset + kept.size, dtype=np.int64)
-            self.mask_rows.append((rows[:, None] * num_feats + feat_cols[None, :]).reshape(-1))
-        self.sizes.append(int(kept.size))
-        self.kept_local.append(kept)
-
-    def build(self, x: Tensor) -> Batch:
-        dev = x.device
-        node_ids = np.concatenate(self.node_ids) if self.node_ids else np.zeros(0, dtype=np.int64)
-        edges = np.concatenate(self.edges, axis=1) if self.edges else np.zeros((2, 0), dtype=np.int64)
-        sizes = np.asarray(self.sizes, dtype=np.int64)
-        ptr = np.zeros(len(self.sizes) + 1, dtype=np.int64)
-        np.cumsum(sizes, out=ptr[1:])
-        xv = x.index_select(0, torch.from_numpy(node_ids).to(dev))
-        if self.mask_rows:
-            flat = torch.from_numpy(np.concatenate(self.mask_rows)).to(dev)
-            xv.view(-1).index_fill_(0, flat, 0.0)
-        batch_vec = torch.from_numpy(np.repeat(np.arange(len(self.sizes), dtype=np.int64), sizes)).to(dev)
-        out = Batch.from_tensors(xv, torch.from_numpy(np.ascontiguousarray(edges)).to(dev), batch_vec,
-                                 torch.from_numpy(ptr).to(dev))
-        out._ptr_host = ptr.tolist()
-        return out
+    def __init__(self, total_nodes: int):
+        self.alive = np.zeros(total_nodes, dtype=bool)      # node kept by the node drop
+        self.edge_picks = {}                                # graph -> positions (permuted) inside its surviving edge block
+        self.feat_cols = {}                                 # graph -> masked feature columns
 
 
-def _plan_view(n: int, edges_local: np.ndarray, num_feats: int, gen: torch.Generator):
-    """One augmented view of one graph (reference augmentations.py:63-74).  Returns (kept nodes ascending,
-    relabelled edges [2, e'], masked feature columns or None)."""
+def _draw_view(view: _ViewDraws, g: int, start: int, n: int, edge_lo: int, edge_hi: int, src: np.ndarray, dst: np.ndarray,
+               num_feats: int, gen: torch.Generator) -> None:
+    """The draws of one augmented view of one graph, in the reference's order (augmentations.py:63-74; App. A.8):
+    randperm(n) -> rand(1) -> [randperm(E')] -> rand(1) -> [randperm(F)]."""
     # node drop (augmentations.py:45-60)
     if n >= NODE_DROP_MIN_NUM_NODES:
         keep = n - max(1, int(n * NODE_DROP_RATE))
-        kept = np.sort(torch.randperm(n, generator=gen)[:keep].numpy())
-        new_id = np.full(n, -1, dtype=np.int64)
-        new_id[kept] = np.arange(kept.size, dtype=np.int64)
-        src, dst = edges_local[0], edges_local[1]
-        alive = (new_id[src] >= 0) & (new_id[dst] >= 0)
-        edges = np.stack([new_id[src[alive]], new_id[dst[alive]]])
+        view.alive[torch.randperm(n, generator=gen)[:keep].numpy() + start] = True
     else:
-        kept = np.arange(n, dtype=np.int64)
-        edges = edges_local
+        view.alive[start:start + n] = True
     # edge drop with probability 0.2 (augmentations.py:30-42,68-69); survivors follow the permutation's order
     if torch.rand(1, generator=gen).item() < EDGE_DROP_PROB:
-        e = edges.shape[1]
+        e = edge_hi - edge_lo
+        if e and n >= NODE_DROP_MIN_NUM_NODES:              # edges that survived this graph's node drop
+            e = int(np.count_nonzero(view.alive[src[edge_lo:edge_hi]] & view.alive[dst[edge_lo:edge_hi]]))
         if e >= EDGE_DROP_MIN_NUM_EDGES:
             keep_e = e - max(1, int(e * EDGE_DROP_RATE))
-            cols = torch.randperm(e, generator=gen)[:keep_e].numpy()
-            edges = edges[:, cols]
+            view.edge_picks[g] = torch.randperm(e, generator=gen)[:keep_e].numpy()
     # attribute mask with probability 0.2 (augmentations.py:17-27,71-72)
-    feat_cols = None
     if torch.rand(1, generator=gen).item() < ATTR_MASK_PROB:
         if num_feats >= ATTR_MASK_MIN_NUM_FEATURES:
             k = max(1, int(num_feats * ATTR_MASK_RATE))
-            feat_cols = torch.randperm(num_feats, generator=gen)[:k].numpy().astype(np.int64)
-    return kept, edges, feat_cols
+            view.feat_cols[g] = torch.randperm(num_feats, generator=gen)[:k].numpy().astype(np.int64)
+
+
+def _assemble_view(view: _ViewDraws, x: Tensor, src: np.ndarray, dst: np.ndarray, graph_of_node: np.ndarray,
+                   graph_of_edge: np.ndarray, num_graphs: int, num_feats: int):
+    """Batch-wide assembly of one view: kept nodes (ascending = grouped by graph), relabelled edges in original order
+    (permuted selections spliced in for the graphs that drew an edge drop), masked attribute cells.  Returns the view
+    Batch and its kept global node ids."""
+    dev = x.device
+    node_ids = np.flatnonzero(view.alive)
+    sizes = np.bincount(graph_of_node[node_ids], minlength=num_graphs).astype(np.int64)
+    ptr = np.zeros(num_graphs + 1, dtype=np.int64)
+    np.cumsum(sizes, out=ptr[1:])
+    new_id = np.cumsum(view.alive, dtype=np.int64) - 1                   # id in the view batch (offsets included)
+    survive = view.alive[src] & view.alive[dst]
+    edges = np.stack([new_id[src[survive]], new_id[dst[survive]]])       # original column order
+    if view.edge_picks:
+        per_graph = np.bincount(graph_of_edge[survive], minlength=num_graphs)
+        block = np.zeros(num_graphs + 1, dtype=np.int64)
+        np.cumsum(per_graph, out=block[1:])
+        pieces, at = [], 0
+        for g in sorted(view.edge_picks):
+            if block[g] > at:
+                pieces.append(np.arange(at, block[g], dtype=np.int64))
+            pieces.append(view.edge_picks[g] + block[g])
+            at = block[g + 1]
+        if edges.shape[1] > at:
+            pieces.append(np.arange(at, edges.shape[1], dtype=np.int64))
+        edges = edges[:, np.concatenate(pieces)] if pieces else edges[:, :0]
+    xv = x.index_select(0, torch.from_numpy(node_ids).to(dev))
+    cells = [(np.arange(ptr[g], ptr[g + 1], dtype=np.int64)[:, None] * num_feats + cols[None, :]).reshape(-1)
+             for g, cols in view.feat_cols.items() if sizes[g]]
+    if cells:
+        xv.view(-1).index_fill_(0, torch.from_numpy(np.concatenate(cells)).to(dev), 0.0)
+    batch_vec = torch.from_numpy(np.repeat(np.arange(num_graphs, dtype=np.int64), sizes)).to(dev)
+    out = Batch.from_tensors(xv, torch.from_numpy(np.ascontiguousarray(edges)).to(dev), batch_vec, torch.from_numpy(ptr).to(dev))
+    out._ptr_host = ptr.tolist()
+    return out, node_ids, sizes
 
 
 class GraphAugmentor:
@@ -118,36 +119,24 @@ class GraphAugmentor:
         order_ok = ei.shape[1] == 0 or bool(np.all(np.diff(graph_of_edge) >= 0))
         if not order_ok:
             raise ValueError('edge_index columns must be grouped by graph (Batch.from_data_list order)')
-        cuts = np.searchsorted(graph_of_edge, np.arange(len(ptr)), side='left')
-        plans = (_ViewPlan(), _ViewPlan())
-        masks_a, masks_b = [], []
-        for g in range(len(ptr) - 1):
+        num_graphs = len(ptr) - 1
+        cuts = np.searchsorted(graph_of_edge, np.arange(len(ptr)), side='left').tolist()
+        total = ptr[-1]
+        src, dst = (ei[0], ei[1]) if ei.shape[1] else (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))
+        views = (_ViewDraws(total), _ViewDraws(total))
+        for g in range(num_graphs):                          # the only per-graph work: the draws themselves
             start, n = ptr[g], ptr[g + 1] - ptr[g]
-            local = ei[:, cuts[g]:cuts[g + 1]] - start
-            views = []
-            for plan in plans:
-                kept, edges, feat_cols = _plan_view(n, local, num_feats, generator)
-                plan.add(start, kept, edges, feat_cols, num_feats)
-                views.append(kept)
-            # augmentations.py:77-85: nodes present in both views (membership through a per-graph bitmap: the kept
-            # sets are subsets of range(n), so this is isin() without its sort/concatenate machinery)
-            in_a, in_b = np.zeros(n, dtype=bool), np.zeros(n, dtype=bool)
-            in_a[views[0]] = True
-            in_b[views[1]] = True
-            masks_a.append(in_b[views[0]])
-            masks_b.append(in_a[views[1]])
-        v1, v2 = plans[0].build(x), plans[1].build(x)
-        # all masks travel in one upload and are handed back as per-graph views of it
-        def to_device(masks):
-            if not masks:
-                return []
-            flat = torch.from_numpy(np.concatenate(masks)).to(dev)
-            return list(torch.split(flat, [m.size for m in masks]))
-        dev_a, dev_b = to_device(masks_a), to_device(masks_b)
-        # rows of each view that survive in both (what NodeContrastiveTask gathers, reference tasks.py:153-164), computed
-        # here from the host masks: the device masks would cost one nonzero() = one device sync per graph and view
-        for view, host_masks, dev_masks in ((v1, masks_a, dev_a), (v2, masks_b, dev_b)):
-            starts = view._ptr_host
-            rows = [np.flatnonzero(m) + starts[g] for g, m in enumerate(host_masks)]
-            view._common_rows_host = (dev_masks, np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64))
+            for view in views:
+                _draw_view(view, g, start, n, cuts[g], cuts[g + 1], src, dst, num_feats, generator)
+        graph_of_node = np.repeat(np.arange(num_graphs, dtype=np.int64), np.diff(np.asarray(ptr, dtype=np.int64)))
+        (v1, ids_a, sizes_a), (v2, ids_b, sizes_b) = (
+            _assemble_view(view, x, src, dst, graph_of_node, graph_of_edge, num_graphs, num_feats) for view in views)
+        # augmentations.py:77-85: nodes present in both views, per graph (one flat membership lookup per view)
+        flat_a, flat_b = views[1].alive[ids_a], views[0].alive[ids_b]
+        dev_a = list(torch.split(torch.from_numpy(flat_a).to(dev), sizes_a.tolist())) if num_graphs else []
+        dev_b = list(torch.split(torch.from_numpy(flat_b).to(dev), sizes_b.tolist())) if num_graphs else []
+        # rows of each view that survive in both (what NodeContrastiveTask gathers, reference tasks.py:153-164), from the
+        # host masks: the device masks would cost one nonzero() = one device sync per graph and view
+        v1._common_rows_host = (dev_a, np.flatnonzero(flat_a))
+        v2._common_rows_host = (dev_b, np.flatnonzero(flat_b))
         return v1, v2, dev_a, dev_b
