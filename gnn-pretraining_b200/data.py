@@ -13,6 +13,8 @@ import torch
 from torch import Tensor
 
 _NODE_OFFSET_KEYS = ('edge_index', 'face')
+_STRUCTURE_KEYS = ('edge_index', 'ptr', 'batch')
+_HOST_MIRRORS = ('_ptr_host', '_edge_index_host', '_common_rows_host')
 
 
 def _offset_key(name: str) -> bool:
@@ -40,10 +42,14 @@ class Data:
     def __setattr__(self, name, value):
         if name.startswith('_'):
             self.__dict__[name] = value
-        elif value is None:
-            self._t.pop(name, None)
         else:
-            self._t[name] = value
+            if name in _STRUCTURE_KEYS:            # host mirrors of the structure (Batch.from_data_list, gnnb200.loader) are stale now
+                for mirror in _HOST_MIRRORS:
+                    self.__dict__.pop(mirror, None)
+            if value is None:
+                self._t.pop(name, None)
+            else:
+                self._t[name] = value
 
     def __getstate__(self):
         return self.__dict__
@@ -127,6 +133,14 @@ class Batch(Data):
                                                   torch.tensor(counts, device=dev))
         out._t['ptr'] = torch.tensor(starts, dtype=torch.long, device=dev)
         out._cuts, out._starts, out._n_graphs = cuts, starts, len(graphs)
+        # Collation happens on the host: keep what the host-side planners (augmentation, negative sampling, node masking)
+        # read — graph boundaries and the edge list — as host mirrors, so that after .to(device) they never have to
+        # read the structure back (one sync + one device->host copy per task and domain otherwise).  Assigning a new
+        # edge_index / ptr / batch drops them (Data.__setattr__).
+        ei = out._t.get('edge_index')
+        if ei is not None and not ei.is_cuda and ei.dtype == torch.long:
+            out._ptr_host = list(starts)
+            out._edge_index_host = ei.numpy()
         return out
 
     @classmethod

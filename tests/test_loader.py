@@ -94,6 +94,8 @@ def test_resident_batches_feed_the_host_planners_without_readback():
     picks = [3, 3, 0, 15, 8, 9, 2, 11]
     mirrored = loader.ResidentDomain(graphs).batch_of(picks)
     plain = Batch.from_data_list([graphs[i] for i in picks])
+    for mirror in ('_edge_index_host', '_ptr_host'):          # force the read-back path for the comparison
+        plain.__dict__.pop(mirror, None)
     assert getattr(plain, '_edge_index_host', None) is None
     for seed in (0, 5):
         a = augment.GraphAugmentor.create_two_views(mirrored, torch.Generator().manual_seed(seed))
@@ -214,3 +216,19 @@ def test_processed_data_round_trip_with_own_classes(tmp_path):
     assert [b.num_graphs for b in val] == [4] and torch.equal(val[0].graph_properties.view(4, 12), props[6:10])
     ft = loader.create_finetune_data_loader('ENZYMES', 'val', 3, torch.Generator(), root=tmp_path)
     assert [b.num_graphs for b in ft] == [3, 1]
+
+
+def test_from_data_list_keeps_host_mirrors_until_the_structure_changes():
+    """Batch.from_data_list on host tensors keeps `_ptr_host` / `_edge_index_host` (what the augmentation, negative-sampling
+    and masking planners read) across .to(device); assigning new structure drops them."""
+    graphs = _graphs('MUTAG', 5, seed=2)
+    b = Batch.from_data_list(graphs)
+    assert b._ptr_host == b.ptr.tolist() and np.array_equal(b._edge_index_host, b.edge_index.numpy())
+    moved = b.to('cpu')
+    assert moved._ptr_host == b.ptr.tolist()
+    c = b.clone()
+    assert np.array_equal(c._edge_index_host, b.edge_index.numpy())
+    b.x = b.x * 2                                            # features may change freely
+    assert hasattr(b, '_edge_index_host')
+    b.edge_index = b.edge_index[:, :3]
+    assert '_edge_index_host' not in b.__dict__ and '_ptr_host' not in b.__dict__
