@@ -324,11 +324,32 @@ def run_product(args):
                     sec['cpu_oracle']['cores'] = torch.get_num_threads()
             except Exception as exc:                      # noqa: BLE001 — reported in the JSON line, not swallowed
                 sec = {'error': f'{type(exc).__name__}: {exc}'}
+            sec['c4_s5_data_parallel_n1'] = c4_in_subprocess()
             out['secondary'] = sec
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+def c4_in_subprocess(steps=10, warmup=3, timeout=420):
+    """BASELINE configs[3] at one replica (`--workload c4`), in its OWN process: the s5 training iteration is the newest
+    code on the device and must not be able to take the headline line down with it.  Returns that run's headline fields."""
+    import subprocess
+    try:
+        torch.cuda.empty_cache()
+        run = subprocess.run([sys.executable, os.path.abspath(__file__), '--workload', 'c4', '--steps', str(steps), '--warmup',
+                              str(warmup)], capture_output=True, text=True, timeout=timeout,
+                             env={k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')})
+        for line in reversed(run.stdout.strip().splitlines()):
+            if line.startswith('{'):
+                js = json.loads(line)
+                return {'steps_per_s': js['value'], 'ms_per_step': js['ms_per_step'],
+                        'graphs_per_s': js['config'].get('graphs_per_sec'), 'e2e_steps_per_s': js['e2e']['value'],
+                        'gpu_launches_per_step': js.get('gpu_launches', 0) / max(steps, 1)}
+        return {'error': (run.stderr.strip().splitlines() or ['no output'])[-1][:300], 'returncode': run.returncode}
+    except Exception as exc:                              # noqa: BLE001 — reported, not swallowed
+        return {'error': f'{type(exc).__name__}: {exc}'[:300]}
 
 
 # ------------------------------------------------------------------------------------------------
