@@ -332,7 +332,7 @@ def run_product(args):
     return out
 
 
-def c4_in_subprocess(steps=10, warmup=3, timeout=420):
+def c4_in_subprocess(steps=10, warmup=3, timeout=180):
     """BASELINE configs[3] at one replica (`--workload c4`), in its OWN process: the s5 training iteration is the newest
     code on the device and must not be able to take the headline line down with it.  Returns that run's headline fields."""
     import subprocess
