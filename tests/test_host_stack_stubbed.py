@@ -199,3 +199,24 @@ def test_long_rows_plumbing(stubbed, monkeypatch):
     seen.clear()
     ops._aggregate_raw(torch.zeros(4, 255), rowptr, col, L.AGG_SUM, None, None, None, long_rows=ids)    # no 128-bit layout
     assert [n for n, _ in seen] == ['gnnb200_aggregate_f32'] and seen[0][1][6] == L.AGG_SUM
+
+
+def test_bench_c4_subprocess_leg_parses_or_reports(monkeypatch):
+    """bench.c4_in_subprocess: the child's JSON line becomes the secondary entry; a child that dies is reported, never raised."""
+    import json
+    import subprocess
+    import types
+    bench = _bench_module()
+    line = {'metric': 'pretrain_steps_per_sec', 'value': 12.5, 'ms_per_step': 80.0, 'gpu_launches': 30000,
+            'config': {'graphs_per_sec': 1600.0}, 'e2e': {'value': 11.0}}
+    monkeypatch.setattr(subprocess, 'run', lambda *a, **k: types.SimpleNamespace(stdout='noise\n' + json.dumps(line) + '\n', stderr='', returncode=0))
+    got = bench.c4_in_subprocess(steps=10)
+    assert got == {'steps_per_s': 12.5, 'ms_per_step': 80.0, 'graphs_per_s': 1600.0, 'e2e_steps_per_s': 11.0,
+                   'gpu_launches_per_step': 3000.0}
+    monkeypatch.setattr(subprocess, 'run', lambda *a, **k: types.SimpleNamespace(stdout='', stderr='Traceback\nRuntimeError: boom', returncode=1))
+    assert bench.c4_in_subprocess()['error'] == 'RuntimeError: boom'
+
+    def hang(*a, **k):
+        raise subprocess.TimeoutExpired('bench', 1)
+    monkeypatch.setattr(subprocess, 'run', hang)
+    assert 'TimeoutExpired' in bench.c4_in_subprocess()['error']
