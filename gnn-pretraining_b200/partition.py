@@ -190,11 +190,16 @@ class PeerRows:
         return self.tables[b]
 
     def close(self) -> None:
+        """Collective: every rank unmaps its peers' buffers, then (after a barrier — freeing exported memory that a peer
+        still has mapped is undefined) frees its own."""
         for p in self._mapped:
             ops._invoke('gnnb200_peer_close', p)
+        self._mapped = []
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
         for p in self._mine:
             ops._invoke('gnnb200_peer_free', p)
-        self._mapped, self._mine = [], []
+        self._mine = []
         PeerRows._cache = {k: v for k, v in PeerRows._cache.items() if v is not self}
 
 
