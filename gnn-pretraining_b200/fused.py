@@ -39,8 +39,7 @@ def _native_usable(h: Tensor, tensors, bn1, bn2, graph, need_t: bool) -> bool:
     return all(t is None or t.is_contiguous() for t in tensors)
 
 
-def _p(t):
-    return None if t is None else t.data_ptr()
+_p = ops._ptr
 
 
 def _native_forward(h, eps, w1, b1, g1, be1, w2, b2, g2, be2, graph, bn1, bn2, training, drop_p, seed, precision):
