@@ -83,17 +83,21 @@ def graph_of(edge_index: Tensor, num_nodes: int) -> Graph:
 
 
 def segment_ptr_of(batch: Tensor, size: Optional[int] = None) -> Tensor:
-    """int32 ptr [B+1] for a sorted ``batch`` vector, cached on the tensor object.  When ``size`` is
-    not given it is read from the last element (one device->host sync, like PyG's
-    ``int(batch.max()) + 1``)."""
+    """int32 ptr [B+1] for a sorted ``batch`` vector, cached on the tensor object per segment count.  When ``size`` is
+    not given it is read from the last element (one device->host sync, like PyG's ``int(batch.max()) + 1``) and
+    remembered, so the sync happens once per tensor."""
     cached = getattr(batch, '_gnnb200_ptr', None)
-    if cached is not None and cached[1] == batch._version and (size is None or cached[0].numel() == size + 1):
-        return cached[0]
+    if cached is None or cached['version'] != batch._version:
+        cached = {'version': batch._version, 'natural': None, 'ptr': {}}
     if size is None:
-        size = int(batch[-1]) + 1 if batch.numel() > 0 else 0
-    ptr = ops.segment_ptr(batch, size)
-    try:
-        setattr(batch, '_gnnb200_ptr', (ptr, batch._version))
-    except AttributeError:
-        pass
+        if cached['natural'] is None:
+            cached['natural'] = int(batch[-1]) + 1 if batch.numel() > 0 else 0
+        size = cached['natural']
+    ptr = cached['ptr'].get(size)
+    if ptr is None:
+        ptr = cached['ptr'][size] = ops.segment_ptr(batch, size)
+        try:
+            setattr(batch, '_gnnb200_ptr', cached)
+        except AttributeError:
+            pass
     return ptr

@@ -220,3 +220,24 @@ def test_bench_c4_subprocess_leg_parses_or_reports(monkeypatch):
         raise subprocess.TimeoutExpired('bench', 1)
     monkeypatch.setattr(subprocess, 'run', hang)
     assert 'TimeoutExpired' in bench.c4_in_subprocess()['error']
+
+
+def test_graph_and_segment_caches(stubbed):
+    """graph_of / segment_ptr_of build once per tensor object and notice in-place edits (`_version`), a different node
+    count and a different segment count; the by-source CSR is built lazily, once."""
+    from gnnb200 import graph as graph_mod
+    ei = torch.randint(0, 50, (2, 300))
+    g1 = graph_mod.graph_of(ei, 50)
+    assert graph_mod.graph_of(ei, 50) is g1 and stubbed['gnnb200_csr_build_i64'] == 1
+    g1.rowptr_t, g1.col_t, g1.rowptr_t                              # noqa: B018 — lazily built, once
+    assert stubbed['gnnb200_csr_build_i64'] == 2
+    assert graph_mod.graph_of(ei, 60) is not g1                      # other node count
+    ei[0, 0] = 7                                                     # in-place edit bumps the tensor's version
+    g2 = graph_mod.graph_of(ei, 60)
+    assert g2._version == ei._version and stubbed['gnnb200_csr_build_i64'] == 4
+    assert graph_mod.graph_of(ei.clone(), 60) is not g2              # another tensor object: its own CSR
+    batch = torch.repeat_interleave(torch.arange(4), torch.tensor([3, 1, 0, 5]))
+    p1 = graph_mod.segment_ptr_of(batch, 4)
+    assert graph_mod.segment_ptr_of(batch, 4) is p1 and stubbed['gnnb200_segment_ptr_i64'] == 1
+    assert graph_mod.segment_ptr_of(batch, 6) is not p1 and stubbed['gnnb200_segment_ptr_i64'] == 2
+    assert graph_mod.segment_ptr_of(batch).numel() == 4 + 1          # size read from the last element (like PyG)
