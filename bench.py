@@ -31,11 +31,18 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+DTYPE_NAMES = {'f32': 'f32', 'tf32': 'f32+tf32', 'tf32x3': 'f32 (dense transforms: 3xTF32 on tcgen05, fp32-class)',
+               'tf32_fwd3': 'f32 storage; forward GEMMs 3xTF32 (fp32-class), backward GEMMs tf32, fp32 accumulate'}
 METRIC = 'aggregated_edges_per_sec_fwd_bwd'
 UNIT = 'edges/s'
 LAYERS = 5
 HIDDEN = 256
 C5_N, C5_E, C5_F = 2_449_029, 61_859_140, 100
+
+
+def gnn_precision():
+    from gnnb200 import nn as gnn
+    return gnn.default_precision()
 
 
 def peaks():
@@ -142,6 +149,72 @@ def step_fn(model, opt, x, edge_index):
     return loss
 
 
+def partition_selfcheck(prod, dev, rank, world, halo):
+    """Parity of the path that is about to be timed, on the hardware it is timed on: a 200 k-node / 5 M-edge graph of the
+    same generator, same seeded model on every rank, dropout off.  All ranks run one node-partitioned forward + backward
+    (+ the flat gradient all-reduce); rank 0 also runs the single-device path and compares: the first layer's
+    aggregation output (pure gather: must be bit-identical), the backbone output (BatchNorm moments are merged in another
+    order across ranks: fp32 rounding), the loss, and the Frobenius error over all parameter gradients.  N = 1 reports
+    the single-device loss of the same graph and seed, so the lines of a scaling run can be read side by side."""
+    import torch.distributed as dist
+    from gnnb200 import partition
+    n, e = 200_000, 5_000_000
+    data = make_graph(n, e, C5_F, 7, 0.5, dev)
+    x, ei = data['x'], data['edge_index']
+    w = torch.randn(n, HIDDEN, device=dev, generator=torch.Generator(device=dev).manual_seed(3))    # fixed read-out
+    old_p = prod.DROPOUT_RATE
+    prod.DROPOUT_RATE = 0.0
+
+    def fresh():
+        m = build_model(prod, dev, C5_F, seed=11)
+        m['input_encoder'].dropout.p = 0.0
+        return m
+    out = {'graph': {'nodes': n, 'edges': e}}
+    try:
+        ref = None
+        if rank == 0:
+            m1 = fresh()
+            h0 = m1['input_encoder'](x)
+            z1 = m1['gnn_backbone'].layers[0].gin_conv.aggregate(h0, ei)
+            h1 = m1['gnn_backbone'](h0, ei)
+            loss1 = (h1 * w).sum()
+            loss1.backward()
+            ref = (z1.detach(), h1.detach(), float(loss1), torch.cat([p.grad.reshape(-1) for p in m1.parameters()]))
+            out['loss_single_device'] = ref[2]
+        if world > 1:
+            m = fresh()
+            graph = partition.PartitionedGraph(ei, n, rank, world, halo=halo)
+            with partition.partition_scope(graph):
+                h0 = m['input_encoder'](x[graph.lo:graph.hi])
+                z = m['gnn_backbone'].layers[0].gin_conv.aggregate(h0, graph)
+                h = m['gnn_backbone'](h0, graph)
+                loss = (h * w[graph.lo:graph.hi]).sum()
+                loss.backward()
+            partition.allreduce_gradients(m)
+            total = loss.detach().clone()
+            dist.all_reduce(total)
+
+            def everyone(t):                               # [n, F] on every rank from the row shards
+                pad = t.new_zeros(graph.per, t.size(1))
+                pad[: t.size(0)] = t
+                full = t.new_empty(graph.per * world, t.size(1))
+                dist.all_gather_into_tensor(full, pad)
+                return full[:n]
+            z_all, h_all = everyone(z.detach()), everyone(h.detach())
+            if rank == 0:
+                g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+                out.update({'halo': graph.halo, 'aggregation_bitwise': bool(torch.equal(z_all, ref[0])),
+                            'fwd_max_rel': float((h_all - ref[1]).abs().max() / ref[1].abs().max()),
+                            'loss_partitioned': float(total), 'loss_rel': abs(float(total) - ref[2]) / abs(ref[2]),
+                            'grad_fro': float((g - ref[3]).norm() / ref[3].norm())})
+                out['ok'] = bool(out['aggregation_bitwise'] and out['fwd_max_rel'] < 1e-3 and out['grad_fro'] < 2e-2)
+    finally:
+        prod.DROPOUT_RATE = old_p
+    del data, x, ei, w
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_product(args):
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -177,9 +250,17 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    selfcheck = None if args.no_selfcheck else partition_selfcheck(prod, dev, rank, world, args.halo)
+
     # ---- device-resident leg -----------------------------------------------------------------
-    for _ in range(args.warmup):
-        one_step(x_dev, ei_dev)
+    loss0 = None
+    for i in range(args.warmup):
+        l_ = one_step(x_dev, ei_dev)
+        if i == 0:                                   # step-0 loss (dropout active: masks depend on the partition)
+            l0 = l_.detach().double().clone()
+            if world > 1:
+                dist.all_reduce(l0)
+            loss0 = float(l0)
     barrier()
     ops.reset_counters()
     ops.AGG_TIMER = []
@@ -222,23 +303,35 @@ def run_product(args):
 
     # Every step's inputs come from pinned host memory and its loss goes back to the host; the copy of
     # step i+1's inputs runs on a side stream while step i computes (double-buffered device inputs).
+    # The two sets of device input buffers are allocated ONCE (a fresh 2 GB allocation per step on the side stream cost
+    # +32 % on a 16-core box in round 1); a set is overwritten only after the step that read it has finished (`done`).
     copy_stream = torch.cuda.Stream(device=dev)
+    slots = [(torch.empty_like(x_host, device=dev), torch.empty_like(ei_host, device=dev)) for _ in range(2)]
+    done = [None, None]
+    turn = [0]
 
     def upload():
+        b = turn[0] & 1
+        turn[0] += 1
+        xd, eid = slots[b]
         with torch.cuda.stream(copy_stream):
-            xd = x_host.to(dev, non_blocking=True)
-            eid = ei_host.to(dev, non_blocking=True)
+            if done[b] is not None:
+                copy_stream.wait_event(done[b])
+            xd.copy_(x_host, non_blocking=True)
+            eid.copy_(ei_host, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
-        return xd, eid, ready
+        return xd, eid, ready, b
 
     pending = [None]
 
+    def finish(b):
+        done[b] = torch.cuda.Event()
+        done[b].record(torch.cuda.current_stream(dev))
+
     def e2e_step():
-        xd, eid, ready = pending[0] if pending[0] is not None else upload()
+        xd, eid, ready, b = pending[0] if pending[0] is not None else upload()
         torch.cuda.current_stream(dev).wait_event(ready)
-        xd.record_stream(torch.cuda.current_stream(dev))
-        eid.record_stream(torch.cuda.current_stream(dev))
         pending[0] = upload()                      # next step's H2D overlaps this step's compute
         if world > 1:
             parts = eid.new_empty(world, 2, eid.size(1))
@@ -248,6 +341,7 @@ def run_product(args):
             loss = one_step(xd, full, True)
         else:
             loss = one_step(xd, eid)
+        finish(b)
         return float(loss.detach().cpu())          # D2H read of the step's result
 
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -288,7 +382,7 @@ def run_product(args):
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': {'f32': 'f32', 'tf32': 'f32+tf32', 'tf32x3': 'f32 (dense transforms: 3xTF32 on tcgen05, fp32-class)'}[gnn.default_precision()],
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': DTYPE_NAMES[gnn.default_precision()],
             'data': 'synthetic',
             'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F,
                        'hidden': HIDDEN, 'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
@@ -303,6 +397,7 @@ def run_product(args):
                     'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4,
                     'note': 'inputs from pinned host memory every step (H2D on a side stream, prefetched one step ahead), loss read back every step'},
             'gpu_launches': launches,
+            'selfcheck': selfcheck, 'loss_step0': loss0,
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30,
             'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM,2,6> (fwd and transposed bwd)',
                          'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
@@ -312,7 +407,7 @@ def run_product(args):
                          'share_of_step': (sum(agg_ms) / ms) if agg_ms else None},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_baseline(args, budget_steps=1)
+            out['cpu_baseline'] = cpu_baseline(args)
         if world == 1 and not args.no_secondary:
             # the small-graph configs are reported beside the headline; a failure there must not lose the headline line
             try:
@@ -561,7 +656,7 @@ def run_c4(args):
                   for b in fixed.values())
         out = {'metric': 'pretrain_steps_per_sec', 'value': 1e3 / ms, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-               'dtype': 'f32+tf32', 'data': 'synthetic',
+               'dtype': DTYPE_NAMES[gnn_precision()], 'data': 'synthetic',
                'config': {'workload': 'c4_s5_data_parallel', 'graphs_per_rank': 128, 'global_batch': 128 * world,
                           'domains': TU_DOMAINS, 'tasks': S5_TASKS, 'graphs_per_sec': 128 * world * 1e3 / ms,
                           'step': 'gnnb200.pretrain.train_step (reference run_training iteration incl. balancer, surgery, metrics)',
@@ -581,15 +676,16 @@ def run_c4(args):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the oracle = the reference's modules restated over the pure-PyTorch PyG shim)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_sizes(args):
-    frac = args.cpu_sample
+def cpu_sample_sizes(args, frac):
     return max(1024, int(C5_N * args.scale * frac)), max(4096, int(C5_E * args.scale * frac))
 
 
-def cpu_run(args, steps, warmup):
+def cpu_run(args, frac, steps, warmup):
+    """The reference's CPU path (oracle port: the reference modules restated over the PyG shim) on a `frac` node/edge
+    sample of the workload, all host threads; returns (n, e, [seconds per timed step])."""
     from oracle import modules as orc
     torch.set_num_threads(os.cpu_count() or 1)
-    n, e = cpu_sample_sizes(args)
+    n, e = cpu_sample_sizes(args, frac)
     data = make_graph(n, e, C5_F, 42, args.locality, 'cpu', args.skew)
     model = build_model(orc, torch.device('cpu'), C5_F)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
@@ -599,37 +695,154 @@ def cpu_run(args, steps, warmup):
         step_fn(model, opt, data['x'], data['edge_index'])
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return n, e, sec
+    return n, e, times
 
 
-def cpu_baseline(args, budget_steps=1):
-    n, e, sec = cpu_run(args, steps=budget_steps, warmup=1)
+def cpu_budget_fraction(args, probe_frac, probe_sec, steps, budget_s, cap):
+    """Largest sample fraction <= cap whose (steps + 1 warm-up) fit `budget_s` seconds (step time is linear in the sample:
+    the CPU path is gather / GEMM bound) and whose transient [E, 256] fp32 message tensors (3 alive at the peak) fit half
+    of the free host memory."""
+    frac = min(cap, probe_frac * budget_s / ((steps + 1) * max(probe_sec, 1e-3)))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        frac = min(frac, 0.5 * avail / (3.0 * C5_E * args.scale * HIDDEN * 4))
+    except Exception:                                     # noqa: BLE001 — no psutil: keep the time bound only
+        pass
+    return max(probe_frac, frac)
+
+
+def cpu_baseline(args):
+    """~20-30 s of CPU work on rank 0: 1 warm-up + 3 timed steps (median) on 1/16 of the workload."""
+    frac = args.cpu_sample or 1.0 / 16
+    n, e, times = cpu_run(args, frac, steps=3, warmup=1)
+    sec = statistics.median(times)
     return {'value': e * LAYERS * 2 / sec, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{n} nodes / {e} edges ({args.cpu_sample:g} of the workload), same model, '
-                      f'{budget_steps} timed step(s) of {sec:.2f} s after 1 warm-up', 'seconds_per_step': sec}
+            'sample': f'{n} nodes / {e} edges ({frac:g} of the workload), same model and step, median of 3 timed steps '
+                      f'({sec:.2f} s) after 1 warm-up', 'seconds_per_step': sec, 'cpu': cpu_model()}
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return None
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the same step on the host cores.  The reference is pure
+    Python over PyTorch-Geometric, which cannot be installed here, so what runs is the oracle port of its
+    modules (pinned bit for bit against the unmodified reference files, tests/test_oracle_reference.py).  Every step is a
+    bounded SAMPLE of the arm's workload: a quarter of the nodes and edges when that fits ~2.5 minutes and the host memory,
+    else the largest fraction that does (probed with one step on 1/16); median over the timed steps."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
-    n, e, sec = cpu_run(args, steps=args.steps, warmup=args.warmup)
+    steps = max(1, args.steps)
+    if args.cpu_sample:
+        frac = args.cpu_sample
+    else:
+        probe = 1.0 / 16
+        _, _, t = cpu_run(args, probe, steps=1, warmup=0)
+        frac = cpu_budget_fraction(args, probe, t[0], steps, budget_s=150.0, cap=0.25)
+    n, e, times = cpu_run(args, frac, steps=steps, warmup=1)
+    sec = statistics.median(times)
     value = e * LAYERS * 2 / sec
-    base = {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{n} nodes / {e} edges ({args.cpu_sample:g} of the workload) per step'}
+    n_full, e_full = max(1024, int(C5_N * args.scale)), max(4096, int(C5_E * args.scale))
+    sample = (f'{n} nodes / {e} edges per step = {frac:.3g} of the workload ({n_full} nodes / {e_full} edges), same model and '
+              f'step; median of {steps} timed steps after 1 warm-up')
+    base = {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample,
+            'cpu': cpu_model(), 'seconds_per_step': sec}
     return {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F, 'hidden': HIDDEN,
-                   'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW on host cores (oracle port of the reference)',
-                   'edge_locality': args.locality, 'degree_skew': args.skew},
+        # the arm's own config (the rate is per edge, so a sample of the workload measures the same metric)
+        'config': {'workload': 'c5_products_backbone', 'nodes': n_full, 'edges': e_full, 'feat_in': C5_F, 'hidden': HIDDEN,
+                   'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
+                   'edge_locality': args.locality, 'degree_skew': args.skew,
+                   'sampled_step': {'nodes': n, 'edges': e, 'fraction': frac,
+                                    'why': 'CPU step on the full graph takes minutes and ~190 GB of transient messages'}},
         'cpu_baseline': base,
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# C1: BASELINE configs[0], the config the reference runs on CPU — `--workload c1`
+# ------------------------------------------------------------------------------------------------
+def run_c1(args):
+    """Cora-shaped backbone forward+backward (N=2,708, E=10,556 directed, F=1,433, H=256) at L=3 (BASELINE) and L=5 (the
+    reference's constant), train mode: gnnb200 on cuda:0 and the oracle port on the host cores, median of `steps` after
+    `warmup`.  Launch-bound on the GPU (the whole graph is L2-resident): reported in ms and edges/s, no roofline."""
+    import gnnb200  # noqa: F401
+    from gnnb200 import models as prod, ops, synthetic
+    from oracle import modules as orc
+    cora = synthetic.cora_like(42)
+    steps, warmup = max(args.steps, 10), max(args.warmup, 3)
+    res = {}
+    for layers in (3, 5):
+        for impl, mods, dev in (('gnnb200', prod, torch.device('cuda', 0)), ('cpu_oracle', orc, torch.device('cpu'))):
+            if impl == 'cpu_oracle':
+                if args.no_cpu_baseline:
+                    continue
+                torch.set_num_threads(os.cpu_count() or 1)
+            torch.manual_seed(0)
+            m = torch.nn.ModuleDict({'input_encoder': mods.InputEncoder(1433, HIDDEN),
+                                     'gnn_backbone': mods.GINBackbone(layers, HIDDEN)}).to(dev)
+            m.train()
+            x_host, ei_host = cora['x'], cora['edge_index']
+            if dev.type == 'cuda':
+                x_host, ei_host = x_host.pin_memory(), ei_host.pin_memory()
+            x, ei = x_host.to(dev), ei_host.to(dev)
+
+            def step(e2e=False):
+                xs, eis = (x_host.to(dev, non_blocking=True), ei_host.to(dev, non_blocking=True)) if e2e else (x, ei.view_as(ei))
+                m.zero_grad(set_to_none=True)
+                loss = m['gnn_backbone'](m['input_encoder'](xs), eis).sum()
+                loss.backward()
+                return float(loss) if e2e else loss
+
+            def timed(e2e):
+                ts = []
+                for i in range(warmup + steps):
+                    if dev.type == 'cuda':
+                        torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    step(e2e)
+                    if dev.type == 'cuda':
+                        torch.cuda.synchronize()
+                    if i >= warmup:
+                        ts.append(time.perf_counter() - t0)
+                return statistics.median(ts)
+            ops.reset_counters()
+            sec = timed(False)
+            entry = {'ms': sec * 1e3, 'edges_per_s': 10556 * layers * 2 / sec}
+            if dev.type == 'cuda':
+                entry['gpu_launches_per_step'] = ops.launch_count() / (warmup + steps)
+                entry['e2e_ms'] = timed(True) * 1e3
+            else:
+                entry['cores'] = torch.get_num_threads()
+            res[f'L{layers}_{impl}'] = entry
+    g = res['L3_gnnb200']
+    out = {'metric': METRIC, 'value': g['edges_per_s'], 'unit': UNIT, 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
+           'ms_per_step': g['ms'], 'higher_is_better': True, 'scaling': 'replicas only', 'vs_baseline': None,
+           'dtype': DTYPE_NAMES[gnn_precision()], 'data': 'synthetic',
+           'config': {'workload': 'c1_cora_backbone', 'nodes': 2708, 'edges': 10556, 'feat_in': 1433, 'hidden': HIDDEN,
+                      'layers': 3, 'mode': 'train fwd+bwd', 'l2_policy': 'working set < L2 (launch-bound; roofline not meaningful)'},
+           'e2e': {'value': 10556 * 3 * 2 / (g['e2e_ms'] / 1e3), 'unit': UNIT, 'ms_per_step': g['e2e_ms'],
+                   'h2d_bytes_per_step': 2708 * 1433 * 4 + 2 * 10556 * 8, 'd2h_bytes_per_step': 4},
+           'gpu_launches': int(g['gpu_launches_per_step'] * steps), 'all': res}
+    if 'L3_cpu_oracle' in res:
+        c = res['L3_cpu_oracle']
+        out['cpu_baseline'] = {'value': c['edges_per_s'], 'unit': UNIT, 'cores': c['cores'], 'kind': 'port',
+                               'sample': f'the whole C1 step, median of {steps}', 'cpu': cpu_model()}
+    return out
 
 
 def main():
@@ -642,16 +855,19 @@ def main():
     ap.add_argument('--locality', type=float, default=0.0, help='fraction of intra-block edges (0 = uniform random)')
     ap.add_argument('--skew', type=float, default=0.0,
                     help='> 1: power-law endpoints (1.8 ~ ogbn-products: largest hub 2.8e-4 of all edges); 0 = uniform (default)')
-    ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3'])
+    ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3', 'tf32_fwd3'])
     ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'auto', 'peer', 'peercopy'],
                     help='N > 1: rows exchanged per layer (default dense = all-gather; see gnnb200/partition.py)')
-    ap.add_argument('--cpu-sample', type=float, default=1.0 / 16, dest='cpu_sample')
+    ap.add_argument('--cpu-sample', type=float, default=None, dest='cpu_sample',
+                    help='fraction of the workload per CPU step (default: 1/16 for cpu_baseline; --impl reference picks up to 1/4 by time and memory)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
+    ap.add_argument('--no-selfcheck', action='store_true', help='profiling runs only: skip the parity check before the timed region')
     ap.add_argument('--no-secondary', action='store_true', help='skip the small-graph configs (C1 backbone, C2 fine-tune step, C3 s4 step)')
     ap.add_argument('--secondary-steps', type=int, default=40, dest='secondary_steps', help='timed steps per small-graph config with --only-secondary')
     ap.add_argument('--only-secondary', action='store_true', help='time only the small-graph configs and print them')
-    ap.add_argument('--workload', default='c5', choices=['c5', 'c4'], help='c5 = headline (default); c4 = data-parallel s5 pre-training step')
+    ap.add_argument('--workload', default='c5', choices=['c5', 'c4', 'c1'],
+                    help='c5 = headline (default); c4 = data-parallel s5 pre-training step; c1 = Cora-shaped backbone, GPU and CPU')
     args = ap.parse_args()
     if args.only_secondary:
         import gnnb200  # noqa: F401
@@ -662,8 +878,8 @@ def main():
             sec['cpu_oracle'] = small_graph_steps('oracle', torch.device('cpu'), steps=4, warmup=1)
         print(json.dumps(sec), flush=True)
         return
-    if args.workload == 'c4':
-        out = run_c4(args)
+    if args.workload in ('c4', 'c1'):
+        out = run_c4(args) if args.workload == 'c4' else run_c1(args)
         if out is not None:
             print(json.dumps(out), flush=True)
         return

@@ -13,7 +13,7 @@ OK, EINVAL, ERANGE, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
 AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
 AGG_ACCUMULATE, AGG_SKIP_LONG, AGG_LONG_ROW = 8, 16, 1024
 POOL_SUM, POOL_MEAN, POOL_MAX = 0, 1, 2
-GEMM_F32, GEMM_TF32, GEMM_AUTO, GEMM_TF32X3, GEMM_AUTO_X3 = 0, 1, 2, 3, 4
+GEMM_F32, GEMM_TF32, GEMM_AUTO, GEMM_TF32X3, GEMM_AUTO_X3, GEMM_AUTO_FWD3 = 0, 1, 2, 3, 4, 5
 EPI_NONE, EPI_RELU = 0, 1
 
 P = c_void_p
@@ -32,7 +32,8 @@ class GinLayerArgs(Structure):
                                   'ds', 'dr1', 'da1', 'dz', 'dw1', 'dw2', 'dgamma1', 'dbeta1', 'dgamma2', 'dbeta2', 'deps')] +
                 [('seed', c_uint64), ('drop_p', c_float), ('momentum1', c_float), ('bn_eps1', c_float),
                  ('momentum2', c_float), ('bn_eps2', c_float), ('training', c_int), ('precision', c_int),
-                 ('need_dh', c_int)])
+                 ('need_dh', c_int), ('x3w_raw_hi', c_int)] +
+                [(k, P) for k in ('w1_hi', 'w1_lo', 'w2_hi', 'w2_lo')])
 
 
 # name -> argtypes, in the order of include/gnnb200.h
@@ -51,6 +52,8 @@ SIGNATURES = {
     'gnnb200_rows_scatter_f32': [P, I64, c_int, P, I64, I64, P, I64, P],
     'gnnb200_rows_gather_bwd_f32': [P, I64, P, P, I64, I64, P, I64, P],
     'gnnb200_gemm_f32': [P, I64, c_int, P, I64, c_int, P, I64, I64, I64, I64, P, P, I64, c_int, c_int, P, P, P, SZP, P],
+    'gnnb200_split_tf32_f32': [P, I64, P, P, P],
+    'gnnb200_linear_x3w_f32': [P, I64, P, P, P, I64, P, I64, I64, I64, I64, P, P, I64, c_int, c_int, P, P, P, SZP, P],
     'gnnb200_colstats_f32': [P, I64, I64, I64, P, P, P, SZP, P],
     'gnnb200_bn_finalize_f32': [P, P, I64, I64, c_float, c_float, P, P, P, P, P],
     'gnnb200_bn_act_fwd_f32': [P, I64, P, P, P, P, c_int, c_float, c_uint64, I64, I64, P, I64, P],
@@ -77,7 +80,7 @@ SIGNATURES = {
     'gnnb200_dev_trace_end': [],
 }
 TRACE_FUNCTIONS = ('gnnb200_aggregate_f32', 'gnnb200_gemm_f32', 'gnnb200_colstats_f32', 'gnnb200_bn_finalize_f32',
-                   'gnnb200_bn_act_fwd_f32', 'gnnb200_bn_act_bwd_f32', 'gnnb200_dot_f32')   # ids of gnnb200_dev_trace_*
+                   'gnnb200_bn_act_fwd_f32', 'gnnb200_bn_act_bwd_f32', 'gnnb200_dot_f32', 'gnnb200_linear_x3w_f32')   # ids of gnnb200_dev_trace_*
 PEER_SHIFT, MAX_PEERS, PEER_HANDLE_BYTES = 28, 16, 64
 
 _lib = None

@@ -292,37 +292,3 @@ extern "C" int gnnb200_aggregate_long_rows_f32(const float* x, int64_t ldx, cons
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
-
-// Development-only tuning hook (not part of include/gnnb200.h): SUM mode, F = 256, 16-byte aligned.
-extern "C" int gnnb200_dev_aggregate_variant(const float* x, const int32_t* rowptr, const int32_t* col, int64_t num_rows,
-                                             const float* eps, float* out, int variant, gnnb200_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const int feat = 256;
-  const int64_t ld = 256;
-#define GNNB200_VARIANT(G, V, U, MINB)                                                                              \
-  {                                                                                                                  \
-    const unsigned grid = (unsigned)((num_rows * G + 255) / 256);                                                    \
-    aggregate_vec_kernel<G, V, GNNB200_AGG_SUM, U, MINB><<<grid, 256, 0, stream>>>(x, ld, rowptr, col, num_rows, feat, \
-                                                                                   x, ld, eps, nullptr, out, ld, 0); \
-  }
-  switch (variant) {
-    case 0: GNNB200_VARIANT(32, 2, 4, 1) break;
-    case 1: GNNB200_VARIANT(32, 2, 4, 4) break;
-    case 2: GNNB200_VARIANT(32, 2, 8, 2) break;
-    case 3: GNNB200_VARIANT(32, 2, 2, 6) break;
-    case 4: GNNB200_VARIANT(16, 4, 4, 2) break;
-    case 5: GNNB200_VARIANT(16, 4, 2, 4) break;
-    case 6: GNNB200_VARIANT(32, 2, 8, 3) break;
-    case 7: GNNB200_VARIANT(32, 2, 2, 4) break;
-    case 8: GNNB200_VARIANT(32, 2, 2, 8) break;
-    case 9: GNNB200_VARIANT(32, 2, 1, 8) break;
-    case 10: GNNB200_VARIANT(32, 2, 3, 6) break;
-    case 11: GNNB200_VARIANT(32, 2, 2, 5) break;
-    case 12: GNNB200_VARIANT(32, 2, 1, 6) break;
-    case 13: GNNB200_VARIANT(32, 2, 3, 5) break;
-    default: return GNNB200_EINVAL;
-  }
-#undef GNNB200_VARIANT
-  GNNB200_LAUNCH_CHECK();
-  return GNNB200_OK;
-}

@@ -1,5 +1,6 @@
-// Column-stationary variants of the BatchNorm(+ReLU+dropout) apply kernels and a vectorised column-statistics
-// kernel (selected by GNNB200_EW_V2=1, see ew_common.cuh).
+// Column-stationary BatchNorm(+ReLU+dropout) apply kernels and the vectorised column-statistics kernel: the kernels
+// gnnb200_bn_act_fwd/bwd_f32 and gnnb200_colstats_f32 launch (bn.cu / reduce.cu keep the first versions for the shapes these
+// do not cover).
 //
 // Why.  Per-launch times of the C5 step at quarter scale (profiles/r01e_launches_scale0.25_tf32.csv; bytes / time against
 // the measured 6.55 TB/s copy peak):
@@ -13,9 +14,11 @@
 // float4) of a 256-row chunk, its 8 warps interleave the rows, the per-column parameters live in registers for the
 // whole chunk, and several rows' 128-bit loads are issued before the first one is consumed.
 //
-// Same arithmetic expressions and the same Philox counter (row * cols/4 + column quad) as the first versions, so the
-// forward output, the regenerated dropout mask and dx are bit-identical to them; the statistics differ from the first
-// version only in the (still fixed) order in which a chunk's partial moments are merged.
+// Same arithmetic expressions and the same Philox counter (row * cols/4 + column quad) as the first versions (the dropout
+// mask does not depend on which kernel ran); the statistics differ from the first version only in the (still fixed) order
+// in which a chunk's partial moments are merged.  Measured on B200, C5 size (2.45 M rows; fraction of the 6.55 TB/s copy
+// peak, first version -> this one): forward C=512 0.95 -> 0.99, forward + dropout 0.66 -> 0.83, backward reduce + apply
+// C=512 0.75 -> 0.97, column statistics 0.62 -> 0.95 (gpurun_out of round 2, profiles/r02_elementwise.md).
 #include "common.cuh"
 #include "ew_common.cuh"
 

@@ -1,7 +1,6 @@
 // Device helpers shared by the elementwise / column-reduction kernels (bn.cu, reduce.cu, elementwise_v2.cu):
 // the counter-based dropout stream, the recomputed BatchNorm/ReLU/dropout gradient mask, Chan's moment merge.
 #pragma once
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace gnnb200 {
@@ -59,17 +58,6 @@ __device__ __forceinline__ Moments merge(Moments a, Moments b) {
   r.sum = a.sum + b.sum;
   r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / n);
   return r;
-}
-
-// GNNB200_EW_V2=1 selects the column-stationary variants of the BatchNorm apply kernels and the vectorised
-// column-statistics kernel (elementwise_v2.cu).  Read once per process.  Off by default: the variants were written
-// after the round-1 GPU budget was spent; they become the default once the suite has run green with them on a B200.
-inline bool ew_v2_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("GNNB200_EW_V2");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
 }
 
 }  // namespace gnnb200

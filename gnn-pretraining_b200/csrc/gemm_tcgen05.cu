@@ -21,7 +21,6 @@
 // epilogue.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the store.
 #include <cuda.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace gnnb200 {
@@ -150,14 +149,19 @@ struct Params {
   long long ldr;
   int relu;
   float* col_part;    // optional [m_tiles*4][3][N] per-32-row (count, sum, centred m2) of the written C columns (BN statistics)
-  int debug;          // dev only (env GNNB200_GEMM_DEBUG): 1 = skip epilogue global stores, 2 = skip the whole epilogue body
 };
 
-// X3 = error-compensated "3xTF32": every operand word v is split in shared memory into hi = v with the 13 low
-// mantissa bits cleared (exactly representable in tf32) and lo = v - hi (exact in fp32), and each K-step issues
-// three MMAs  hi*hi + hi*lo + lo*hi  into the same fp32 accumulator: the dropped lo*lo term and the tf32
-// truncation of lo are ~2^-21 relative, i.e. fp32-class results from the tf32 tensor pipe.
-template <int BN, bool X3>
+// X3 = error-compensated "3xTF32": every operand word v is split into hi = v with the 13 low mantissa bits cleared
+// (exactly representable in tf32) and lo = v - hi (exact in fp32), and each K-step issues three MMAs
+// hi*hi + hi*lo + lo*hi  into the same fp32 accumulator: the dropped lo*lo term and the tf32 truncation of lo are
+// ~2^-21 relative, i.e. fp32-class results from the tf32 tensor pipe.  Where the split happens:
+//   X3 = 1  both operands in shared memory by the splitter warps (any layout; used by precision 'tf32x3')
+//   X3 = 2  B arrives pre-split from global memory (two tensor maps: hi, lo — a weight matrix, split once per optimizer
+//           step); the splitter warps rewrite only the A tile (hi in place + lo twin)
+//   X3 = 3  as 2, but the raw fp32 tiles serve as the hi operands (kind::tf32 reads only the upper 19 bits of each word —
+//           checked bit for bit by tests/test_gpu_gemm.py::test_tf32_mma_truncates_operands), so the splitter only WRITES
+//           lo(A) and the hi*hi / hi*lo(B) MMAs of a stage start as soon as TMA has landed it
+template <int BN, int X3>
 struct TileCfg {
   static constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
   static constexpr uint32_t kBBytes = BN * BK * 4;
@@ -170,22 +174,23 @@ struct TileCfg {
   static_assert(kStages >= 2, "tile does not fit shared memory");
 };
 
-// TMA_ST (opt-in, GNNB200_GEMM_TMA_STORE=1; plain tf32, no split-K, no residual, no fused statistics): the epilogue's
+// TMA_ST (plain tf32 without split-K, residual or fused statistics; measured on B200: C5 step 243.3 -> 239.1 ms): the epilogue's
 // XOR-swizzled 32x32 staging tile IS the SWIZZLE_128B box layout, so instead of reading it back and issuing
 // st.global the warp applies bias/ReLU on the TMEM side, and one lane hands the tile to the TMA unit
 // (cp.async.bulk.tensor store, clipped at the matrix edge by the tensor map).
-template <int BN, bool A_MN, bool B_MN, bool X3, bool TMA_ST = false>
+template <int BN, bool A_MN, bool B_MN, int X3, bool TMA_ST = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, const Params p) {
-  static_assert(!(TMA_ST && X3), "the TMA-store epilogue exists for the plain tf32 kernel only");
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_blo, const Params p) {
+  static_assert(!(TMA_ST && X3 != 0), "the TMA-store epilogue exists for the plain tf32 kernel only");
+  static_assert(X3 < 2 || (!A_MN && !B_MN), "pre-split B: nn.Linear forward layout only (A [M,K], B [N,K])");
   using Cfg = TileCfg<BN, X3>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kABytes = Cfg::kABytes;
   constexpr uint32_t kBBytes = Cfg::kBBytes;
   constexpr uint32_t kHiBytes = Cfg::kHiBytes;
   constexpr uint32_t kStageBytes = Cfg::kStageBytes;
-  constexpr int kEpi = X3 ? 4 : kEpiWarps;            // epilogue warps
+  constexpr int kEpi = X3 != 0 ? 4 : kEpiWarps;       // epilogue warps
   constexpr int kSplit = 6;                           // splitter warps (X3 only)
   constexpr uint32_t kSlabBytes = BK * 128;   // MN-major: one 32-wide slab = BK rows x 128 B
   constexpr uint32_t kIdesc = make_idesc(BN, A_MN, B_MN);
@@ -252,8 +257,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kHiBytes);
+          mbar_expect_tx(&full_bar[stage], X3 >= 2 ? kHiBytes + kBBytes : kHiBytes);
           const int k0 = kb * BK;
+          if constexpr (X3 >= 2) tma_load_2d(&map_blo, &full_bar[stage], sb + kHiBytes, k0, n0);   // lo(B) twin tile
           if (A_MN) {
 #pragma unroll
             for (int s = 0; s < BM / 32; ++s) tma_load_2d(&map_a, &full_bar[stage], sa + s * kSlabBytes, m0 + 32 * s, k0);
@@ -284,10 +290,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(X3 ? &split_bar[stage] : &full_bar[stage], phase);
+          mbar_wait((X3 == 1 || X3 == 2) ? &split_bar[stage] : &full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
+          if constexpr (X3 == 3) {
+            // raw tiles are the hi operands: two of the three products need nothing from the splitter warps
+            const uint64_t lo_off = (uint64_t)(kHiBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+              const uint64_t db = make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
+              umma_tf32(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);             // hi(A) * hi(B)
+              umma_tf32(d_tmem, da, db + lo_off, kIdesc, 1u);                               // hi(A) * lo(B)
+            }
+            mbar_wait(&split_bar[stage], phase);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+              const uint64_t db = make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
+              umma_tf32(d_tmem, da + lo_off, db, kIdesc, 1u);                               // lo(A) * hi(B)
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA (K=8 tf32) advances 32 B inside
@@ -307,6 +332,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               umma_tf32(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
+          }   // X3 != 3
           umma_commit(&empty_bar[stage]);              // frees the smem stage once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -314,7 +340,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (X3 && (warp == 2 || warp == 3 || warp >= 8)) {
+  } else if (X3 != 0 && (warp == 2 || warp == 3 || warp >= 8)) {
     // ===================== operand splitter (X3 only): hi/lo decomposition in shared memory =====================
     {
       const int tid_s = (warp < 4 ? warp - 2 : warp - 6) * 32 + lane;      // 0 .. kSplit*32-1
@@ -327,8 +353,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&full_bar[stage], phase);                 // TMA bytes have landed (hi region holds raw fp32)
           uint4* hi = reinterpret_cast<uint4*>(smem + stage * kStageBytes);
           uint4* lo = reinterpret_cast<uint4*>(smem + stage * kStageBytes + kHiBytes);
+          constexpr int kSplitVecs = (int)((X3 == 1 ? kHiBytes : kABytes) / 16);   // pre-split B: only the A tile
 #pragma unroll 4
-          for (int i = tid_s; i < (int)(kHiBytes / 16); i += kSplit * 32) {
+          for (int i = tid_s; i < kSplitVecs; i += kSplit * 32) {
             const uint4 v = hi[i];
             uint4 h, l;
             h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
@@ -336,7 +363,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
             l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
             l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-            hi[i] = h;
+            if constexpr (X3 != 3) hi[i] = h;
             lo[i] = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -371,16 +398,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int c4 = (lane & 7) << 2;                  // column (floats) inside the 32-wide chunk
       const int c_begin = half * kChunksPerWarp, c_end = c_begin + kChunksPerWarp;
       uint32_t v[32];
-      if (p.debug != 2) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_begin * 32), v);
-      } else {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      }
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c_begin * 32), v);
       if constexpr (TMA_ST) {
 #pragma unroll 1
-        for (int c = c_begin; c < (p.debug == 2 ? c_begin : c_end); ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           if (lane == 0) tma_store_wait_read();          // the previous chunk's store has drained the staging tile
           __syncwarp();
           tmem_ld_wait();
@@ -405,14 +426,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
           __syncwarp();
-          if (lane == 0 && p.debug != 1) {
+          if (lane == 0) {
             tma_store_2d(&map_c, stage, col0, m0 + q * 32);                // rows >= M / columns >= N are clipped
             tma_store_commit();
           }
         }
       } else {   // st.global epilogue (body below keeps its indentation)
 #pragma unroll 1
-      for (int c = c_begin; c < (p.debug == 2 ? c_begin : c_end); ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         const int col = n0 + c * 32 + c4;
         // residual rows for this chunk are requested first so their latency hides behind the TMEM load and the
         // transpose (8 independent 128-bit loads per lane, coalesced: 4 full 128-byte segments per instruction)
@@ -456,7 +477,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
               }
             }
-            if (p.debug != 1) *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
+            *reinterpret_cast<float4*>(cbase + (long long)row * p.ldc + col) = o;
           } else {
             o = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -546,6 +567,17 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long mn
   *reinterpret_cast<float4*>(C + m * ldc + n) = acc;
 }
 
+// hi = v with the 13 low mantissa bits cleared, lo = v - hi (both exact): the pre-split form of a weight matrix
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -595,49 +627,58 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
   return GNNB200_OK;
 }
 
-static int pick_bn(long long N, bool x3) {
-  if (!x3 && N % 256 == 0) return 256;
+static int pick_bn(long long N, int x3) {
+  // x3 = 1 (both operands split in shared memory): 128-wide tiles (a 256-wide stage would leave one pipeline stage);
+  // x3 >= 2 (B pre-split): 256-wide tiles with a two-stage ring — every A tile is split once, not once per 128 columns
+  const bool wide = x3 != 1;
+  if (wide && N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
   if (N % 64 == 0) return 64;
-  if (!x3 && N >= 256) return 256;   // ragged last tile: TMA zero-fills, the store masks (N % 4 == 0 required)
+  if (wide && N >= 256) return 256;   // ragged last tile: TMA zero-fills, the store masks (N % 4 == 0 required)
   if (N >= 128) return 128;
   return 64;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool X3, bool TMA_ST>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Params& p, int grid,
-                  cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, int X3, bool TMA_ST>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mblo,
+                  const Params& p, int grid, cudaStream_t stream) {
   constexpr size_t smem = TileCfg<BN, X3>::kSmemBytes;
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device (a process-wide flag would leave a second GPU of the same process unconfigured);
+  // racing threads at worst set it twice
+  static bool configured[64] = {};
+  int dev = 0;
+  GNNB200_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST><<<grid, kThreads, smem, stream>>>(ma, mb, mc, p);
+  gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST><<<grid, kThreads, smem, stream>>>(ma, mb, mc, mblo, p);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
 
-template <int BN, bool X3, bool TMA_ST = false>
+template <int BN, int X3, bool TMA_ST = false>
 static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
-                     const Params& p, int grid, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<BN, false, false, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
-  if (!a_mn && b_mn) return launch<BN, false, true, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
-  if (a_mn && !b_mn) return launch<BN, true, false, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
-  return launch<BN, true, true, X3, TMA_ST>(ma, mb, mc, p, grid, stream);
-}
-
-// GNNB200_GEMM_TMA_STORE=1: TMA-store epilogue for the GEMMs it covers (read once; opt-in until measured)
-static bool tma_store_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("GNNB200_GEMM_TMA_STORE");
-    return e && atoi(e) != 0;
-  }();
-  return on;
+                     const CUtensorMap& mblo, const Params& p, int grid, cudaStream_t stream) {
+  if constexpr (X3 >= 2) {
+    return launch<BN, false, false, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);   // checked by the caller
+  } else {
+    if (!a_mn && !b_mn) return launch<BN, false, false, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);
+    if (!a_mn && b_mn) return launch<BN, false, true, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);
+    if (a_mn && !b_mn) return launch<BN, true, false, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);
+    return launch<BN, true, true, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);
+  }
 }
 
 }  // namespace tc
+
+int split_tf32(const float* x, int64_t n, float* hi, float* lo, cudaStream_t stream) {
+  if (n <= 0) return GNNB200_OK;
+  tc::split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n, hi, lo);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
 
 int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
                         const float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* residual,
@@ -652,12 +693,15 @@ int gemm_tf32_supported(const float* A, int64_t lda, int transa, const float* B,
   return tc::encode_fn() != nullptr;
 }
 
-int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb, float* C,
+// x3: 0 plain tf32, 1 3xTF32 with both operands split in shared memory, 2 / 3 3xTF32 with B pre-split (B = hi, B_lo = lo;
+// layout transa = 0, transb = 1 only; 3 = B holds the raw weights and the raw tiles act as hi operands)
+int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, const float* B_lo, int64_t ldb, int transb, float* C,
               int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, const float* residual, int64_t ldr,
               int epilogue, int x3, float* col_sum, float* col_m2, void* workspace, size_t* workspace_bytes,
               cudaStream_t stream) {
   using namespace tc;
-  const int bn = pick_bn(N, x3 != 0);
+  if (x3 >= 2 && (transa != 0 || transb == 0 || (workspace && !B_lo))) return GNNB200_EINVAL;
+  const int bn = pick_bn(N, x3);
   const int m_tiles = (int)((M + BM - 1) / BM);
   const int n_tiles = (int)((N + bn - 1) / bn);
   const int k_blocks = (int)((K + BK - 1) / BK);
@@ -706,30 +750,39 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, int64_t l
   p.ldr = ldr;
   p.relu = (splits == 1 && (epilogue & GNNB200_EPI_RELU)) ? 1 : 0;
   p.col_part = col_part;
-  {
-    const char* dbg = getenv("GNNB200_GEMM_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
   const long long total = tiles * splits;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
   // TMA-store epilogue: C as a tensor map of 32x32 boxes in the staging tile's swizzle (inner = N, outer = M)
-  const bool tma_st = !x3 && splits == 1 && !p.residual && !p.col_part && tma_store_enabled();
+  const bool tma_st = !x3 && splits == 1 && !p.residual && !p.col_part;
   CUtensorMap mc = ma;                                   // unused unless tma_st
   if (tma_st) {
     rc = make_map(&mc, C, N, M, ldc, 32, false);
     if (rc) return rc;
   }
-  if (x3) {
-    if (bn == 128) rc = launch_bn<128, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
-    else rc = launch_bn<64, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+  CUtensorMap mblo = mb;                                 // unused unless B arrives pre-split
+  if (x3 >= 2) {
+    rc = make_map(&mblo, B_lo, K, N, ldb, bn, false);
+    if (rc) return rc;
+  }
+  if (x3 == 1) {
+    if (bn == 128) rc = launch_bn<128, 1>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else rc = launch_bn<64, 1>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+  } else if (x3 == 2) {
+    if (bn == 256) rc = launch_bn<256, 2>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, 2>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else rc = launch_bn<64, 2>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+  } else if (x3 == 3) {
+    if (bn == 256) rc = launch_bn<256, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else rc = launch_bn<64, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
   } else if (tma_st) {
-    if (bn == 256) rc = launch_bn<256, false, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
-    else if (bn == 128) rc = launch_bn<128, false, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
-    else rc = launch_bn<64, false, true>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    if (bn == 256) rc = launch_bn<256, 0, true>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, 0, true>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else rc = launch_bn<64, 0, true>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
   } else {
-    if (bn == 256) rc = launch_bn<256, false>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
-    else if (bn == 128) rc = launch_bn<128, false>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
-    else rc = launch_bn<64, false>(a_mn, b_mn, ma, mb, mc, p, grid, stream);
+    if (bn == 256) rc = launch_bn<256, 0>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else if (bn == 128) rc = launch_bn<128, 0>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    else rc = launch_bn<64, 0>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
   }
   if (rc) return rc;
   if (splits > 1) {

@@ -13,7 +13,7 @@
 namespace gnnb200 {
 namespace {
 
-enum FnId { kAggregate = 0, kGemm, kColstats, kBnFinalize, kBnFwd, kBnBwd, kDot };
+enum FnId { kAggregate = 0, kGemm, kColstats, kBnFinalize, kBnFwd, kBnBwd, kDot, kLinearX3w };
 
 // Development trace: between gnnb200_dev_trace_begin/_end the composites RECORD their calls (function id, argument
 // count, arguments as 64-bit words) instead of making them.  Per thread; lets a CPU-only test check the plumbing.
@@ -72,6 +72,17 @@ int gemm_bytes(const gnnb200_gin_layer_t* a, const float* A, int64_t lda, int ta
                           a->precision, nullptr, nullptr, nullptr, out, nullptr);
 }
 
+// forward GEMMs under GNNB200_GEMM_AUTO_FWD3 run on the pre-split weights
+bool fwd3(const gnnb200_gin_layer_t* a) { return a->precision == GNNB200_GEMM_AUTO_FWD3; }
+
+int linear_bytes(const gnnb200_gin_layer_t* a, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t ldy, int64_t M,
+                 int64_t N, int64_t K, const float* residual, int64_t ldr, size_t* out) {
+  if (fwd3(a))
+    return gnnb200_linear_x3w_f32(X, ldx, W, nullptr, nullptr, ldw, nullptr, ldy, M, N, K, nullptr, residual, ldr,
+                                  GNNB200_EPI_NONE, a->x3w_raw_hi, nullptr, nullptr, nullptr, out, nullptr);
+  return gemm_bytes(a, X, ldx, 0, W, ldw, 1, ldy, M, N, K, residual, ldr, out);
+}
+
 bool bad_common(const gnnb200_gin_layer_t* a, const size_t* ws_bytes) {
   return !a || !ws_bytes || a->num_rows < 0 || a->hidden <= 0 || a->mid <= 0 || a->ldh < a->hidden;
 }
@@ -107,9 +118,9 @@ extern "C" int gnnb200_gin_layer_fwd_f32(const gnnb200_gin_layer_t* a, void* wor
   float* m22 = train ? ws.take<float>((size_t)C) : nullptr;
   Scratch sc;
   size_t b = 0;
-  GNNB200_TRY(gemm_bytes(a, a->z, C, 0, a->w1, C, 1, H, n, H, C, nullptr, 0, &b));
+  GNNB200_TRY(linear_bytes(a, a->z, C, a->w1, C, H, n, H, C, nullptr, 0, &b));
   sc.need(b);
-  GNNB200_TRY(gemm_bytes(a, a->r1, H, 0, a->w2, H, 1, C, n, C, H, a->h, a->ldh, &b));
+  GNNB200_TRY(linear_bytes(a, a->r1, H, a->w2, H, C, n, C, H, a->h, a->ldh, &b));
   sc.need(b);
   if (train) {
     GNNB200_TRY(gnnb200_colstats_f32(nullptr, H, n, H, nullptr, nullptr, nullptr, &b, nullptr));
@@ -126,6 +137,7 @@ extern "C" int gnnb200_gin_layer_fwd_f32(const gnnb200_gin_layer_t* a, void* wor
   if (!a->rowptr || !a->h || !a->w1 || !a->w2 || !a->gamma1 || !a->beta1 || !a->gamma2 || !a->beta2 || !a->z || !a->a1 ||
       !a->r1 || !a->s || !a->out || !a->mean1 || !a->invstd1 || !a->mean2 || !a->invstd2)
     return GNNB200_EINVAL;
+  if (fwd3(a) && (!a->w1_lo || !a->w2_lo || (!a->x3w_raw_hi && (!a->w1_hi || !a->w2_hi)))) return GNNB200_EINVAL;
   if (n == 0) return GNNB200_OK;
 
   // z = A h + (1 + eps) h
@@ -133,6 +145,10 @@ extern "C" int gnnb200_gin_layer_fwd_f32(const gnnb200_gin_layer_t* a, void* wor
                    a->eps, nullptr, a->z, C, stream));
   // a1 = z W1^T + b1
   b = sc.bytes;
+  if (fwd3(a))
+    GNNB200_TRY(call(kLinearX3w, gnnb200_linear_x3w_f32, a->z, C, a->w1, a->w1_hi, a->w1_lo, C, a->a1, H, n, H, C, a->b1, nullptr,
+                     0, GNNB200_EPI_NONE, a->x3w_raw_hi, nullptr, nullptr, scratch, &b, stream));
+  else
   GNNB200_TRY(call(kGemm, gnnb200_gemm_f32, a->z, C, 0, a->w1, C, 1, a->a1, H, n, H, C, a->b1, nullptr, 0, GNNB200_EPI_NONE,
                    a->precision, nullptr, nullptr, scratch, &b, stream));
   if (train) {
@@ -146,6 +162,10 @@ extern "C" int gnnb200_gin_layer_fwd_f32(const gnnb200_gin_layer_t* a, void* wor
                    a->r1, H, stream));
   // s = r1 W2^T + b2 + h
   b = sc.bytes;
+  if (fwd3(a))
+    GNNB200_TRY(call(kLinearX3w, gnnb200_linear_x3w_f32, a->r1, H, a->w2, a->w2_hi, a->w2_lo, H, a->s, C, n, C, H, a->b2, a->h,
+                     a->ldh, GNNB200_EPI_NONE, a->x3w_raw_hi, nullptr, nullptr, scratch, &b, stream));
+  else
   GNNB200_TRY(call(kGemm, gnnb200_gemm_f32, a->r1, H, 0, a->w2, H, 1, a->s, C, n, C, H, a->b2, a->h, a->ldh,
                    GNNB200_EPI_NONE, a->precision, nullptr, nullptr, scratch, &b, stream));
   if (train) {

@@ -22,14 +22,15 @@ from . import graph as graph_mod
 from . import ops
 from .graph import Graph
 
-# GNNB200_NATIVE_LAYER=1: issue a layer pass's launches from C++ (gnnb200_gin_layer_fwd/bwd_f32, csrc/gin_layer.cu) instead
-# of one ctypes call per kernel.  Same entry points, same arguments, same order (tests/test_native_layer_trace.py compares
-# the two call sequences on CPU); what changes is host time — a small-graph step is launch-bound and ~80 % of its
-# launches are inside GIN layers.  Opt-in until it has run once on a GPU.
-NATIVE_LAYER = os.environ.get('GNNB200_NATIVE_LAYER', '0') == '1'
+# A layer pass's launches are issued from C++ (gnnb200_gin_layer_fwd/bwd_f32, csrc/gin_layer.cu) instead of one ctypes call
+# per kernel.  Same entry points, same arguments, same order (tests/test_native_layer_trace.py compares the two call
+# sequences on CPU); what changes is host time — a small-graph step is launch-bound and ~80 % of its launches are inside
+# GIN layers.  Measured on B200 (profiles/r02/a_variants.md): C2 fine-tune step 271 -> 361 steps/s, C3 s4 step 10.7 -> 14.1,
+# C4 s5 step 6.9 -> 8.5.  GNNB200_NATIVE_LAYER=0 selects the per-kernel Python path.
+NATIVE_LAYER = os.environ.get('GNNB200_NATIVE_LAYER', '1') == '1'
 
 
-def _native_usable(h: Tensor, tensors, bn1, bn2, graph, need_t: bool) -> bool:
+def _native_usable(h: Tensor, tensors, bn1, bn2, graph, need_t: bool, precision: int = 0) -> bool:
     """Layouts the composite assumes: dense parameters, fp32 rows, standard BatchNorm buffers, no per-launch timing."""
     if ops.AGG_TIMER is not None or h.dtype != torch.float32 or bn1.running_mean is None or bn2.running_mean is None:
         return False
@@ -52,6 +53,9 @@ def _native_forward(h, eps, w1, b1, g1, be1, w2, b2, g2, be2, graph, bn1, bn2, t
                        eps=_p(eps), w1=_p(w1), b1=_p(b1), gamma1=_p(g1), beta1=_p(be1), w2=_p(w2), b2=_p(b2), gamma2=_p(g2),
                        beta2=_p(be2), z=_p(z), a1=_p(a1), r1=_p(r1), s=_p(s), out=_p(out), seed=seed, drop_p=drop_p,
                        training=int(training), precision=precision)
+    if precision == L.GEMM_AUTO_FWD3:
+        (hi1, lo1), (hi2, lo2) = ops.split_weight(w1), ops.split_weight(w2)      # cached until the optimizer touches them
+        a.w1_hi, a.w1_lo, a.w2_hi, a.w2_lo, a.x3w_raw_hi = _p(hi1), _p(lo1), _p(hi2), _p(lo2), int(ops.X3W_RAW_HI)
     if training:
         mean1, invstd1, mean2, invstd2 = new(H), new(H), new(C), new(C)
         for bn, k in ((bn1, '1'), (bn2, '2')):
@@ -107,17 +111,17 @@ class GINLayerFn(torch.autograd.Function):
         h = ops._rowmajor(h)
         ctx.graph, ctx.cfg = graph, (training, drop_p, seed, precision)
         ctx.native = NATIVE_LAYER and _native_usable(h, (eps, w1, b1, g1, be1, w2, b2, g2, be2), bn1, bn2, graph,
-                                                     training and h.requires_grad)
+                                                     training and h.requires_grad, precision)
         if ctx.native:
             out, saved = _native_forward(h, eps, w1, b1, g1, be1, w2, b2, g2, be2, graph, bn1, bn2, training, drop_p, seed,
                                          precision)
             ctx.save_for_backward(h, eps, w1, g1, be1, w2, g2, be2, *saved)
             return out
         z = ops._aggregate_raw(h, graph.rowptr, graph.col, L.AGG_SUM, h, eps, None, long_rows=getattr(graph, 'long_rows', None))
-        a1 = ops._gemm_raw(z, False, w1, True, b1, False, precision)
+        a1 = ops._linear_fwd_raw(z, w1, b1, False, precision)
         mean1, invstd1 = _stats(bn1, a1, training)
         r1 = ops.bn_act.fn(a1, mean1, invstd1, g1, be1, True, 0.0, 0, training, 0)
-        s = ops._gemm_raw(r1, False, w2, True, b2, False, precision, h)
+        s = ops._linear_fwd_raw(r1, w2, b2, False, precision, h)
         mean2, invstd2 = _stats(bn2, s, training)
         out = ops.bn_act.fn(s, mean2, invstd2, g2, be2, True, drop_p, seed, training, 0)
         ctx.save_for_backward(h, eps, w1, g1, be1, w2, g2, be2, z, a1, r1, s, mean1, invstd1, mean2, invstd2)

@@ -12,11 +12,12 @@ from . import ops
 
 _ATTR = '_gnnb200_graph'
 
-# GNNB200_LONG_ROWS=1: graphs with at least LONG_ROW_MIN_EDGES edges are checked for rows with more than L.AGG_LONG_ROW
-# neighbours (one nonzero() = one device sync per CSR build); those rows then take the block-per-row kernel instead of one
-# warp's serial walk (a 17,000-neighbour hub of a products-like graph would otherwise run ~8 ms on its own).  Opt-in until
-# measured; batches of small graphs never pay the sync.
-LONG_ROWS = os.environ.get('GNNB200_LONG_ROWS', '0') == '1'
+# Graphs with at least LONG_ROW_MIN_EDGES edges are checked for rows with more than L.AGG_LONG_ROW neighbours (one nonzero()
+# = one device sync per CSR build; batches of small graphs never pay it); those rows then take the block-per-row kernel
+# instead of one warp's serial walk.  Measured on B200, C5 size with the power-law generator (skew 1.8, ~150 hubs, largest
+# 17 k neighbours): 12.56 -> 9.95 ms per aggregation pass, 254.6 -> 237.0 ms per step (profiles/r02/a_variants.md).
+# GNNB200_LONG_ROWS=0 turns the split off.
+LONG_ROWS = os.environ.get('GNNB200_LONG_ROWS', '1') == '1'
 LONG_ROW_MIN_EDGES = 1 << 16
 
 
@@ -34,7 +35,9 @@ class Graph:
     the fp32 sums bit-identical to the CPU scatter_add_ order."""
 
     def __init__(self, edge_index: Tensor, num_nodes: int):
-        self.edge_index = edge_index
+        # a second tensor object over the same storage: the cache attribute lives on the caller's object, so holding that
+        # one here would close a reference cycle and keep the CSR buffers alive until the cyclic GC runs
+        self.edge_index = edge_index.detach()
         self.num_nodes = int(num_nodes)
         self.num_edges = int(edge_index.size(1))
         self.rowptr, self.col, _ = ops.csr_build(edge_index, self.num_nodes, False)   # the edge permutation is not kept

@@ -11,10 +11,11 @@ from . import _lib as L
 from . import ops
 from .graph import graph_of, segment_ptr_of
 
-# Default arithmetic of the dense transforms: 'tf32' = tcgen05 tensor cores (kind::tf32, fp32 accumulate;
-# the north star's 2e-2 tolerance class) wherever TMA's layout rules hold, FFMA elsewhere;
-# 'f32' = FFMA everywhere (1e-5 class).
-_default_precision = 'tf32'
+# Default arithmetic of the dense transforms: 'tf32_fwd3' = tcgen05 tensor cores (kind::tf32, fp32 accumulate) wherever
+# TMA's layout rules hold, FFMA elsewhere; the forward GEMM of every Linear error-compensated (3xTF32 on pre-split weights,
+# fp32-class activations), backward GEMMs plain tf32: end-to-end gradients inside the north star's 2e-2 class
+# (ops.PRECISIONS).  'tf32' = plain tf32 everywhere; 'tf32x3' = compensated everywhere; 'f32' = FFMA everywhere (1e-5 class).
+_default_precision = 'tf32_fwd3'
 # node-partitioned execution (gnnb200.partition.partition_scope sets this to the rank's PartitionedGraph)
 _partition = None
 

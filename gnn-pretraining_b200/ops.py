@@ -7,6 +7,7 @@ the aggregation, the amax-rule scatter for max pooling, GEMMs for the linears). 
 or eager fallback: CPU tensors raise.
 """
 import ctypes
+import os
 from ctypes import byref, c_size_t
 from typing import List, Optional, Tuple
 
@@ -74,7 +75,8 @@ KERNELS_PER_CALL = {
     'gnnb200_csr_build_i64': 2, 'gnnb200_segment_ptr_i64': 1, 'gnnb200_coalesce_i64': 3,
     'gnnb200_aggregate_f32': 1, 'gnnb200_aggregate_long_rows_f32': 1, 'gnnb200_dot_f32': 2, 'gnnb200_segment_pool_fwd_f32': 1,
     'gnnb200_segment_pool_bwd_f32': 1, 'gnnb200_rows_gather_f32': 1, 'gnnb200_rows_scatter_f32': 1,
-    'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_colstats_f32': 2,
+    'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_linear_x3w_f32': 1, 'gnnb200_split_tf32_f32': 1,
+    'gnnb200_colstats_f32': 2,
     'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
@@ -535,8 +537,64 @@ rows_scatter.register_autograd(_rs_backward, setup_context=_rs_setup)
 # ---------------------------------------------------------------------------------------------
 # 'tf32' = tensor cores wherever the layout rules hold, FFMA elsewhere (e.g. N == 1, ld % 4 != 0);
 # 'tf32_strict' raises instead of taking the FFMA kernel.
+# 'tf32_fwd3' (the default): nn.Linear forward passes in 3xTF32 with the weights split once per optimizer step
+# (gnnb200_linear_x3w_f32), backward GEMMs in plain tf32.  The forward activations decide the ReLU masks of the backward pass:
+# plain tf32 there flips enough of them to push end-to-end gradients past 2e-2 (scripts/precision_study.py: 2.4e-2 .. 1e-1),
+# plain tf32 in dX / dW alone stays at 3e-3 .. 6e-3.
 PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_AUTO, 'tf32_strict': L.GEMM_TF32,
-              'tf32x3': L.GEMM_AUTO_X3, 'tf32x3_strict': L.GEMM_TF32X3}
+              'tf32x3': L.GEMM_AUTO_X3, 'tf32x3_strict': L.GEMM_TF32X3, 'tf32_fwd3': L.GEMM_AUTO_FWD3}
+# raw weights as the hi operand (kind::tf32 reads only the upper 19 bits of a word): the splitter warps then only write lo(A)
+X3W_RAW_HI = os.environ.get('GNNB200_X3W_RAW_HI', '0') == '1'
+
+
+def split_weight(w: Tensor) -> Tuple[Optional[Tensor], Tensor]:
+    """(hi, lo) of a weight matrix for gnnb200_linear_x3w_f32, cached on the tensor until it is modified in place
+    (an optimizer step bumps `_version`) or re-allocated."""
+    key = (w._version, w.data_ptr(), X3W_RAW_HI)
+    cached = getattr(w, '_gnnb200_split', None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    src = w.detach()
+    hi, lo = torch.empty_like(src), torch.empty_like(src)
+    L.check(_invoke('gnnb200_split_tf32_f32', _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _stream(src)), 'split_tf32')
+    if X3W_RAW_HI:
+        hi = None
+    w._gnnb200_split = (key, hi, lo)
+    return hi, lo
+
+
+def _linear_fwd_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor], relu: bool, precision: int,
+                    residual: Optional[Tensor] = None, want_stats: bool = False):
+    """y = x W^T (+bias)(+residual)(ReLU), W [out, in]: the forward GEMM of every Linear.  Under GEMM_AUTO_FWD3 it runs the
+    error-compensated kernel on the pre-split weights; any other precision is _gemm_raw."""
+    if precision != L.GEMM_AUTO_FWD3:
+        return _gemm_raw(x, False, weight, True, bias, relu, precision, residual, want_stats)
+    _need_cuda(x, weight, bias, residual)
+    x, weight = _rowmajor(x), _rowmajor(weight)
+    M, K = x.shape
+    N = weight.size(0)
+    if K != weight.size(1):
+        raise L.Gnnb200Error(f'linear inner dimensions differ: {K} vs {weight.size(1)}')
+    if not weight.is_contiguous():
+        weight = weight.contiguous()
+    hi, lo = split_weight(weight)
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if bias is not None:
+        bias = bias.contiguous()
+    if residual is not None:
+        residual = _rowmajor(residual)
+        if residual.shape != y.shape:
+            raise L.Gnnb200Error(f'residual shape {tuple(residual.shape)} != output shape {tuple(y.shape)}')
+    csum = cm2 = None
+    if want_stats:
+        csum = torch.empty(N, dtype=torch.float32, device=x.device)
+        cm2 = torch.empty(N, dtype=torch.float32, device=x.device)
+    _call_ws('gnnb200_linear_x3w_f32', 'linear (3xTF32, pre-split weights)', x.device, _ptr(x), _ld(x), _ptr(weight),
+             _ptr(hi), _ptr(lo), K, _ptr(y), _ld(y), M, N, K, _ptr(bias), _ptr(residual),
+             _ld(residual) if residual is not None else 0, L.EPI_RELU if relu else L.EPI_NONE, int(X3W_RAW_HI), _ptr(csum),
+             _ptr(cm2), stream=_stream(x),
+             key=(M, N, K, _ld(x) % 4, residual is None or _ld(residual) % 4 == 0, x.data_ptr() % 16, want_stats))
+    return (y, csum, cm2) if want_stats else y
 
 
 def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[Tensor], relu: bool,
@@ -622,7 +680,7 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int,
     into a training-mode BatchNorm: d(loss)/d(bias) is then identically zero (the batch mean absorbs any
     constant shift), so the backward writes zeros instead of reducing grad_y over its rows (the reference
     computes the same quantity numerically and gets rounding noise around 0)."""
-    return _gemm_raw(x, False, weight, True, bias, False, precision, residual)
+    return _linear_fwd_raw(x, weight, bias, False, precision, residual)
 
 
 @linear.register_fake
@@ -661,7 +719,7 @@ def linear_stats(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: i
                  bias_feeds_norm: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """(y, colsum(y), centred second moment of y's columns): `linear` whose GEMM epilogue also produces the batch
     statistics of the BatchNorm that consumes y (no separate read pass over y)."""
-    return _gemm_raw(x, False, weight, True, bias, False, precision, residual, True)
+    return _linear_fwd_raw(x, weight, bias, False, precision, residual, True)
 
 
 @linear_stats.register_fake
@@ -814,6 +872,9 @@ def _(grad_y, x, mean, invstd, gamma, beta, dgamma_dbeta, relu, drop_p, seed, ro
 def _bn_setup(ctx, inputs, output):
     x, mean, invstd, gamma, beta, relu, drop_p, seed, training, rows_total = inputs
     ctx.cfg = (relu, drop_p, seed, training, rows_total)
+    # the group the forward's statistics were reduced over: the backward must reduce dgamma/dbeta over the same one even
+    # when it runs after partition_scope() has been left (e.g. loss.backward() outside the scope)
+    ctx.group = SYNC_GROUP if rows_total > 0 else None
     ctx.save_for_backward(x, mean, invstd, gamma, beta)
 
 
@@ -821,11 +882,15 @@ def _bn_backward(ctx, gy):
     x, mean, invstd, gamma, beta = ctx.saved_tensors
     relu, drop_p, seed, training, rows_total = ctx.cfg
     gy = gy.contiguous()
-    if rows_total > 0 and training and SYNC_GROUP is not None:
+    if rows_total > 0 and training:
+        group = getattr(ctx, 'group', None)
+        if group is None:
+            raise L.Gnnb200Error('bn_act: the forward ran on a row shard (rows_total > 0) without a process group; '
+                                 'the single-device backward would use local sums against global statistics')
         import torch.distributed as dist
         local = bn_act_bwd_reduce(gy, x, mean, invstd, gamma, beta, relu, drop_p, seed)
         total = local.clone()
-        dist.all_reduce(total, group=SYNC_GROUP)
+        dist.all_reduce(total, group=group)
         gx = bn_act_bwd_apply(gy, x, mean, invstd, gamma, beta, total, relu, drop_p, seed, rows_total)
         # parameter gradients stay per-shard partial sums: the flat gradient all-reduce adds them up
         return gx, None, None, local[0], local[1], None, None, None, None, None

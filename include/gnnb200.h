@@ -151,12 +151,29 @@ int gnnb200_rows_gather_bwd_f32(const float* grad_out, int64_t ldg, const int32_
 #define GNNB200_GEMM_AUTO 2 /* TF32 tensor path when the layout allows it, else the fp32 FFMA kernel */
 #define GNNB200_GEMM_TF32X3 3 /* error-compensated 3xTF32 on the tensor pipe: fp32-class (1e-5) accuracy */
 #define GNNB200_GEMM_AUTO_X3 4 /* TF32X3 when the layout allows it, else the fp32 FFMA kernel */
+#define GNNB200_GEMM_AUTO_FWD3 5 /* the default of the modules: nn.Linear FORWARD passes go through gnnb200_linear_x3w_f32 (3xTF32,
+                                    weights pre-split), every other GEMM (dX, dW, similarity matrices) is GNNB200_GEMM_AUTO;
+                                    passed to gnnb200_gemm_f32 itself it means GNNB200_GEMM_AUTO */
 #define GNNB200_EPI_NONE 0
 #define GNNB200_EPI_RELU 1
 int gnnb200_gemm_f32(const float* A, int64_t lda, int transa, const float* B, int64_t ldb, int transb,
                      float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
                      const float* residual, int64_t ldr, int epilogue, int precision, float* col_sum,
                      float* col_m2, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+
+/* nn.Linear forward  Y = X W^T (+bias)(+residual)(ReLU)  in error-compensated 3xTF32 with the weight matrix split ONCE
+ * (gnnb200_split_tf32_f32: hi = w with the 13 low mantissa bits cleared, lo = w - hi; redo it after every optimizer
+ * step) instead of inside every tile: fp32-class activations from the tf32 tensor pipe.  This is what the forward passes of
+ * src/models/gnn.py:13,31,34 and src/models/heads.py:41 run under the default precision: the ReLU masks of the backward
+ * pass are decided by these outputs, and plain tf32 there flips enough of them to put the end-to-end gradients outside
+ * the 2e-2 class (tests/test_gpu_models.py), while plain tf32 in the backward GEMMs does not.
+ * X [M,K] (ldx), W / W_hi / W_lo [N,K] (ldw), Y [M,N].  raw_hi != 0: W itself is read as the hi operand (kind::tf32 ignores
+ * the 13 low mantissa bits; W_hi may be NULL).  Layouts the tensor-core kernel cannot take run the fp32 FFMA kernel on W. */
+int gnnb200_split_tf32_f32(const float* x, int64_t n, float* hi, float* lo, gnnb200_stream_t stream);
+int gnnb200_linear_x3w_f32(const float* X, int64_t ldx, const float* W, const float* W_hi, const float* W_lo,
+                           int64_t ldw, float* Y, int64_t ldy, int64_t M, int64_t N, int64_t K, const float* bias,
+                           const float* residual, int64_t ldr, int epilogue, int raw_hi, float* col_sum,
+                           float* col_m2, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
 
 /* Column statistics over rows (K4 BatchNorm1d batch stats of src/models/gnn.py:15,32,38 and bias
  * gradients): sum[c] = sum_r x[r,c]; when sumsq != NULL also the centred second moment
@@ -305,6 +322,10 @@ typedef struct gnnb200_gin_layer {
   uint64_t seed;
   float drop_p, momentum1, bn_eps1, momentum2, bn_eps2;
   int training, precision, need_dh;
+  /* precision == GNNB200_GEMM_AUTO_FWD3: the two forward GEMMs are gnnb200_linear_x3w_f32 calls on these pre-split weights
+   * (gnnb200_split_tf32_f32; w*_hi may be NULL when x3w_raw_hi != 0); the backward GEMMs stay gnnb200_gemm_f32 */
+  int x3w_raw_hi;
+  const float *w1_hi, *w1_lo, *w2_hi, *w2_lo;
 } gnnb200_gin_layer_t;
 int gnnb200_gin_layer_fwd_f32(const gnnb200_gin_layer_t* layer, void* workspace, size_t* workspace_bytes,
                               gnnb200_stream_t stream);
@@ -312,7 +333,8 @@ int gnnb200_gin_layer_bwd_f32(const gnnb200_gin_layer_t* layer, void* workspace,
                               gnnb200_stream_t stream);
 /* Development hook (per thread): between _begin and _end the two composites record the calls they would make as
  * 64-bit words (function id, argument count, arguments) instead of making them; _end returns the word count
- * (-1 = buffer too small).  Function ids: 0 aggregate, 1 gemm, 2 colstats, 3 bn_finalize, 4 bn_act_fwd, 5 bn_act_bwd, 6 dot. */
+ * (-1 = buffer too small).  Function ids: 0 aggregate, 1 gemm, 2 colstats, 3 bn_finalize, 4 bn_act_fwd, 5 bn_act_bwd, 6 dot,
+ * 7 linear_x3w. */
 int gnnb200_dev_trace_begin(uint64_t* buf, size_t capacity_words);
 long long gnnb200_dev_trace_end(void);
 

@@ -74,6 +74,13 @@ BAD = [
      L.EINVAL),                                                                                 # unknown precision
     ('gnnb200_gemm_f32', (D, 7, 0, D, 8, 1, D, 8, 8, 8, 7, None, None, 0, 0, L.GEMM_TF32, None, None, None, 'SZ', None),
      L.EUNSUPPORTED),                                                                           # lda % 4 != 0: not TMA-legal
+    ('gnnb200_split_tf32_f32', (D, -1, D, D, None), L.EINVAL),
+    ('gnnb200_split_tf32_f32', (D, 16, None, D, None), L.EINVAL),                               # hi == NULL
+    ('gnnb200_linear_x3w_f32', (D, 8, D, D, D, 8, D, 8, -1, 8, 8, None, None, 0, 0, 0, None, None, None, 'SZ', None), L.EINVAL),
+    ('gnnb200_linear_x3w_f32', (D, 8, D, D, D, 8, D, 8, 8, 8, 8, None, None, 0, 0, 0, None, None, None, None, None), L.EINVAL),
+    ('gnnb200_linear_x3w_f32', (D, 8, D, D, D, 8, D, 8, BIG, 8, 8, None, None, 0, 0, 0, None, None, None, 'SZ', None), L.ERANGE),
+    ('gnnb200_linear_x3w_f32', (D, 8, D, None, D, 8, D, 8, 8, 8, 8, None, None, 0, 0, 0, None, None, D, 'SZ', None),
+     L.EINVAL),                                                                                 # no W_hi although raw_hi == 0
     ('gnnb200_colstats_f32', (D, 256, -1, 256, D, D, None, 'SZ', None), L.EINVAL),
     ('gnnb200_colstats_f32', (D, 256, 10, 1 << 24, D, D, None, 'SZ', None), L.ERANGE),
     # ---- BatchNorm ----

@@ -145,9 +145,6 @@ def test_large_graph_properties():
     assert torch.equal(za, ops.gin_aggregate(a, eps, gr.rowptr, gr.col, empty, empty))
 
 
-@pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
-                    reason='peer-memory gather kernel: written after the round-1 GPU budget was spent '
-                           '(set GNNB200_RUN_UNVERIFIED=1)')
 @pytest.mark.parametrize('n,e,f,world', [(1000, 9000, 256, 4), (257, 3000, 128, 8), (2708, 10556, 512, 2),
                                          (300, 2000, 64, 3), (64, 0, 256, 2), (999, 8000, 1024, 5)])
 def test_peer_gather_equals_single_device(n, e, f, world):
@@ -180,8 +177,6 @@ def test_peer_gather_equals_single_device(n, e, f, world):
         assert torch.equal(no_self, ops.aggregate(x, gr.rowptr, gr.col, L.AGG_SUM)[lo:hi])
 
 
-@pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
-                    reason='long-row kernel: written after the round-1 GPU budget was spent (set GNNB200_RUN_UNVERIFIED=1)')
 @pytest.mark.parametrize('f', [256, 64, 512, 1024])
 def test_long_rows_take_the_block_per_row_kernel(monkeypatch, f):
     """A graph with three hubs (5,000 / 1,500 / 1,025 in-neighbours, one of them also a source hub) among ordinary rows:
@@ -201,7 +196,7 @@ def test_long_rows_take_the_block_per_row_kernel(monkeypatch, f):
     want = scatter(x.index_select(0, ei[0]), ei[1], dim=0, dim_size=n, reduce='sum') + (1 + eps) * x
     want_t = scatter(x.index_select(0, ei[1]), ei[0], dim=0, dim_size=n, reduce='sum') + (1 + eps) * x
     plain = Graph(ei.to(DEV), n)
-    assert plain.long_rows is None
+    assert plain.long_rows is None                                         # below LONG_ROW_MIN_EDGES: never checked
     monkeypatch.setattr(graph_mod, 'LONG_ROWS', True)
     monkeypatch.setattr(graph_mod, 'LONG_ROW_MIN_EDGES', 1)
     gr = Graph(ei.to(DEV).clone(), n)

@@ -13,9 +13,7 @@ import gnnb200  # noqa: F401
 from gnnb200 import finetune, models, synthetic
 from gnnb200.data import Data
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
-                                 reason='not yet run on a GPU (set GNNB200_RUN_UNVERIFIED=1)')]
+pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda')
 
 

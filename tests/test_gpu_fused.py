@@ -15,6 +15,7 @@ DEV = torch.device('cuda')
 
 
 def _run(fused, train, prec, graphs, seed=5):
+    old = gnn.default_precision()
     gnn.set_default_precision(prec)
     prod.GINLayer.fused = fused
     try:
@@ -32,11 +33,11 @@ def _run(fused, train, prec, graphs, seed=5):
         return logits.detach(), x.grad.clone(), grads, stats
     finally:
         prod.GINLayer.fused = True
-        gnn.set_default_precision('tf32')
+        gnn.set_default_precision(old)
 
 
 @pytest.mark.parametrize('train', [True, False])
-@pytest.mark.parametrize('prec', ['f32', 'tf32'])
+@pytest.mark.parametrize('prec', ['f32', 'tf32', 'tf32_fwd3'])
 def test_fused_layer_equals_op_level_path(train, prec):
     graphs = synthetic.tu_like_graphs('ENZYMES', 24, seed=3)
     a = _run(True, train, prec, graphs)

@@ -1,9 +1,5 @@
 """Dense transforms: fp32 FFMA path within 1e-5 (relative to the output scale) of torch fp32 on the
 CPU; all operand layouts, ragged sizes, split-K, bias/ReLU epilogues, and nn.Linear autograd."""
-import os
-import subprocess
-import sys
-
 import pytest
 import torch
 
@@ -207,6 +203,87 @@ def test_gemm_tf32x3_split_k_and_residual():
     assert _rel(got, torch.relu(dy.double() @ w.double().t() + res.double())) < TOL_F32
 
 
+# ---- 3xTF32 with pre-split weights: the forward GEMM of every Linear under the default precision 'tf32_fwd3' -------------
+def _trunc_tf32(t):
+    return (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+def test_tf32_mma_truncates_operands():
+    """kind::tf32 reads the upper 19 bits of each fp32 word (sign, exponent, 10 mantissa bits) and ignores the rest: a GEMM
+    on operands with the 13 low mantissa bits cleared gives the same BITS as on the raw operands.  gnnb200_linear_x3w_f32's
+    raw_hi mode (X3 = 3 in csrc/gemm_tcgen05.cu) relies on this to use the raw tiles as the hi operands."""
+    g = torch.Generator().manual_seed(21)
+    for m, n, k, ta, tb in ((640, 256, 256, False, True), (300, 512, 96, False, False), (512, 128, 320, True, False)):
+        a = torch.randn((k, m) if ta else (m, k), generator=g).to(DEV)
+        b = torch.randn((n, k) if tb else (k, n), generator=g).to(DEV)
+        prec = ops.PRECISIONS['tf32_strict']
+        raw = ops.gemm(a, ta, b, tb, None, False, prec)
+        assert torch.equal(raw, ops.gemm(_trunc_tf32(a), ta, _trunc_tf32(b), tb, None, False, prec))
+        assert not torch.equal(a, _trunc_tf32(a))
+
+
+def test_split_weight_is_exact_and_cached():
+    w = torch.randn(512, 256, device=DEV)
+    ops.X3W_RAW_HI, old = False, ops.X3W_RAW_HI
+    try:
+        hi, lo = ops.split_weight(w)
+        assert torch.equal(hi, _trunc_tf32(w)) and torch.equal(hi + lo, w)
+        assert float(lo.abs().max()) <= float(w.abs().max()) * 2.0 ** -10
+        assert ops.split_weight(w)[1] is lo                       # cached on the tensor
+        w.mul_(1.5)                                               # an optimizer step bumps the version counter
+        hi2, lo2 = ops.split_weight(w)
+        assert lo2 is not lo and torch.equal(hi2 + lo2, w)
+    finally:
+        ops.X3W_RAW_HI = old
+
+
+@pytest.mark.parametrize('raw_hi', [False, True])
+@pytest.mark.parametrize('m,n,k', [(128, 256, 32), (4100, 512, 256), (4100, 256, 512), (333, 256, 100), (1000, 64, 96),
+                                   (777, 100, 256), (20000, 256, 256), (1, 256, 256), (70001, 512, 256), (513, 128, 768),
+                                   (300, 40, 64), (50, 256, 1433), (128, 1, 256)])
+def test_linear_x3w_is_fp32_class(monkeypatch, raw_hi, m, n, k):
+    """Forward of a Linear under 'tf32_fwd3': 3xTF32 with the weights split once (gnnb200_linear_x3w_f32, both split modes),
+    bias / residual / ReLU epilogues, ragged tiles; layouts TMA cannot take (K % 4 != 0, N = 1) fall to the FFMA kernel."""
+    monkeypatch.setattr(ops, 'X3W_RAW_HI', raw_hi)
+    g = torch.Generator().manual_seed(m + 5 * n + 11 * k)
+    x = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g)
+    bias = torch.randn(n, generator=g)
+    res = torch.randn(m, n, generator=g)
+    prec = ops.PRECISIONS['tf32_fwd3']
+    want = x.double() @ w.double().t() + bias.double()
+    xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
+    assert _rel(ops._linear_fwd_raw(xd, wd, bd, False, prec), want) < TOL_F32
+    assert _rel(ops._linear_fwd_raw(xd, wd, bd, True, prec, res.to(DEV)), torch.relu(want + res.double())) < TOL_F32
+    y, s, m2 = ops._linear_fwd_raw(xd, wd, bd, False, prec, None, True)
+    yd = y.double().cpu()
+    assert _rel(y, want) < TOL_F32 and _rel(s, yd.sum(0)) < 1e-5 and _rel(m2, ((yd - yd.mean(0)) ** 2).sum(0)) < 1e-4
+
+
+def test_linear_autograd_tf32_fwd3():
+    """The default precision: forward in the fp32 class, backward GEMMs plain tf32 (5e-3 per op)."""
+    g = torch.Generator().manual_seed(4)
+    ref = torch.nn.Linear(256, 512)
+    lin = Linear(256, 512)
+    lin.precision = 'tf32_fwd3'
+    lin.load_state_dict(ref.state_dict())
+    lin = lin.to(DEV)
+    x = torch.randn(9000, 256, generator=g)
+    go = torch.randn(9000, 512, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).backward(go)
+    xg = x.to(DEV).requires_grad_(True)
+    y = lin(xg)
+    y.backward(go.to(DEV))
+    assert _rel(y, ref(x).detach()) < TOL_F32
+    assert _rel(xg.grad, xr.grad) < 5e-3
+    assert _rel(lin.weight.grad, ref.weight.grad) < 5e-3
+    with torch.no_grad():
+        lin.weight.add_(0.25)                                     # the cached split must follow the weights
+        ref.weight.add_(0.25)
+    assert _rel(lin(x.to(DEV)), ref(x).detach()) < TOL_F32
+
+
 @pytest.mark.parametrize('prec', ['tf32_strict', 'tf32x3_strict', 'f32'])
 @pytest.mark.parametrize('m,n,k', [(4100, 512, 256), (70001, 256, 512), (333, 256, 100), (31, 64, 64)])
 def test_gemm_epilogue_column_statistics(prec, m, n, k):
@@ -227,36 +304,21 @@ def test_gemm_epilogue_column_statistics(prec, m, n, k):
 
 _TMA_STORE_CASES = [(128, 256, 32, False, True, True, False), (4100, 512, 256, False, True, True, True),
                     (333, 256, 100, False, False, True, False), (777, 100, 256, False, True, False, True),
-                    (129, 8, 40, True, False, True, True), (20000, 256, 256, False, True, True, False),
+                    (132, 8, 40, True, False, True, True), (20000, 256, 256, False, True, True, False),
                     (5000, 128, 64, True, True, False, False), (1, 256, 256, False, True, True, True),
                     (70001, 512, 256, False, True, True, False)]
 
 
-def _tma_store_outputs():
-    outs = []
-    for m, n, k, ta, tb, with_bias, relu in _TMA_STORE_CASES:
-        g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
-        a = torch.randn((k, m) if ta else (m, k), generator=g)
-        b = torch.randn((n, k) if tb else (k, n), generator=g)
-        bias = torch.randn(n, generator=g) if with_bias else None
-        outs.append(ops.gemm(a.to(DEV), ta, b.to(DEV), tb, None if bias is None else bias.to(DEV), relu,
-                             ops.PRECISIONS['tf32_strict']).cpu())
-    return outs
-
-
-@pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
-                    reason='TMA-store epilogue (GNNB200_GEMM_TMA_STORE=1): written after the round-1 GPU budget was spent')
-def test_gemm_tma_store_epilogue_is_bit_identical(tmp_path):
-    """Same accumulators, same bias add and ReLU, only the way the tile leaves the SM differs: the opt-in TMA-store
-    epilogue must reproduce the st.global epilogue bit for bit (ragged M / N edges are clipped by the tensor map).
-    The switch is read once per process, so the TMA leg runs in a child process."""
-    want = _tma_store_outputs()
-    out = tmp_path / 'tma.pt'
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ('import sys, importlib.util, torch; sys.path.insert(0, %r); '
-            's = importlib.util.spec_from_file_location("gemm_cases", %r); t = importlib.util.module_from_spec(s); '
-            's.loader.exec_module(t); torch.save(t._tma_store_outputs(), %r)') % (root, os.path.abspath(__file__), str(out))
-    subprocess.run([sys.executable, '-c', code], check=True, timeout=600, env=dict(os.environ, GNNB200_GEMM_TMA_STORE='1'))
-    got = torch.load(out)
-    for case, w, g_ in zip(_TMA_STORE_CASES, want, got):
-        assert torch.equal(w, g_), case
+@pytest.mark.parametrize('m,n,k,ta,tb,with_bias,relu', _TMA_STORE_CASES)
+def test_gemm_tma_store_epilogue_is_bit_identical(m, n, k, ta, tb, with_bias, relu):
+    """Same accumulators, same bias add and ReLU, only the way the tile leaves the SM differs: the TMA-store epilogue (what
+    a plain tf32 GEMM without residual takes) must reproduce the st.global epilogue bit for bit, ragged M / N edges
+    included (clipped by the tensor map).  A residual of zeros forces the st.global epilogue: x + 0.0 == x exactly."""
+    g = torch.Generator().manual_seed(m + 3 * n + 7 * k)
+    a = torch.randn((k, m) if ta else (m, k), generator=g).to(DEV)
+    b = torch.randn((n, k) if tb else (k, n), generator=g).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV) if with_bias else None
+    prec = ops.PRECISIONS['tf32_strict']
+    via_tma = ops._gemm_raw(a, ta, b, tb, bias, relu, prec)
+    via_st_global = ops._gemm_raw(a, ta, b, tb, bias, relu, prec, torch.zeros(m, n, device=DEV))
+    assert torch.equal(via_tma, via_st_global)

@@ -7,10 +7,15 @@ Tolerances (every individual kernel is checked at 1e-5 / bit-exact / 5e-3 for tf
     the two implementations take different branches of the kink (measured: one such flip in layer 3 of the
     Cora-shaped run moves the upstream gradients by ~1e-3) -> relative Frobenius error <= 5e-3 and at most
     2 % of the entries off by more than 2e-3 of the tensor's scale.
-  * precision 'tf32' (tcgen05 kind::tf32, the north star's 2e-2 class): activations and losses within 2e-2
-    (measured 2e-3); gradients through 5 x (BN, ReLU) compound the per-op 1e-3 noise through many more kink
-    flips (measured relative Frobenius error 3-7 %), so they are held to 1.5e-1 here and the per-op bound is
-    enforced in tests/test_gpu_gemm.py."""
+  * precision 'tf32_fwd3' (the default: forward GEMMs 3xTF32 on pre-split weights, backward GEMMs plain tcgen05
+    kind::tf32 — the north star's 2e-2 class): activations and losses in the fp32 class (2e-4), gradients within 2e-2
+    relative Frobenius error (scripts/precision_study.py: 3e-3 .. 6e-3 expected from tf32 dX / dW).
+  * plain 'tf32' in the FORWARD pass is not an end-to-end configuration: its 1e-3 activation noise flips enough ReLU
+    masks through 5 x (BN, ReLU) to put the gradients at 3-7 % (round 1; reproduced on CPU by the same script), which is
+    why the default compensates the forward GEMMs.  The plain-tf32 kernels are held to their per-op bound in
+    tests/test_gpu_gemm.py and enter the end-to-end tests through the backward pass of 'tf32_fwd3'.
+  * test_error_against_fp64_oracle states the same bars against an fp64 run of the oracle, next to what the fp32 oracle
+    itself achieves against fp64 (the inherent ReLU-kink / summation-order noise floor)."""
 import os
 import random
 
@@ -27,13 +32,13 @@ from oracle import modules as orc
 pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda')
 # fp32 FFMA GEMMs: 1e-5 class per op, compounded end to end; tcgen05 tf32 GEMMs: the north star's 2e-2 class.
-TOLS = {'f32': (2e-4, 2e-3), 'tf32x3': (2e-4, 2e-3), 'tf32': (2e-2, 2e-2)}
-FRO = {'f32': 5e-3, 'tf32x3': 5e-3, 'tf32': 1.5e-1}
+TOLS = {'f32': (2e-4, 2e-3), 'tf32x3': (2e-4, 2e-3), 'tf32_fwd3': (2e-4, 2e-2)}
+FRO = {'f32': 5e-3, 'tf32x3': 5e-3, 'tf32_fwd3': 2e-2}
 FRO_TOL = FRO['f32']
 ACT_TOL, GRAD_TOL = TOLS['f32']
 
 
-@pytest.fixture(params=['f32', 'tf32x3', 'tf32'], autouse=True)
+@pytest.fixture(params=['f32', 'tf32x3', 'tf32_fwd3'], autouse=True)
 def precision(request):
     from gnnb200 import nn as gnn
     global ACT_TOL, GRAD_TOL, FRO_TOL
@@ -116,7 +121,7 @@ def test_finetune_enzymes_against_reference_golden():
     for k, v in g['grads'].items():
         if k.endswith('eps'):
             # d(eps) = sum(g * x) is ONE cancelling sum over every element: relative error is the per-element error
-            # amplified by the cancellation (FFMA 1e-3, 3xTF32 1e-2 measured); meaningless under plain tf32 noise
+            # amplified by the cancellation (FFMA 1e-3, 3xTF32 1e-2 measured); meaningless under tf32 noise in g
             if FRO_TOL < 1e-2:
                 assert _rel(params[k].grad, v) < 3e-2, k
             continue
@@ -221,3 +226,48 @@ def test_train_mode_dropout_runs_and_is_seeded():
     torch.manual_seed(1)
     y2 = m(batch)
     assert torch.equal(y1, y2) and torch.isfinite(y1).all()
+
+
+def test_error_against_fp64_oracle(precision):
+    """The bar stated against ground truth: the product's error against an fp64 run of the oracle, next to the fp32 oracle's
+    own error against the same fp64 run (summation order and ReLU-kink flips: the floor any fp32 implementation sits on).
+    fp32 class: product within 2x the fp32 oracle's error or 5e-3 Frobenius, whichever is larger (a single kink flip moves a
+    gradient by ~1e-3); tensor-core class ('tf32_fwd3'): 2e-2 Frobenius on every gradient, 2e-4 on the logits."""
+    import copy
+    graphs = synthetic.tu_like_graphs('ENZYMES', 16, seed=0)
+    a32 = orc.FinetuneGNN(torch.device('cpu'), 'ENZYMES', 'full_finetune')
+    sd = seeded_state_dict(a32, 3)
+    a32.load_state_dict(sd)
+    a64 = orc.FinetuneGNN(torch.device('cpu'), 'ENZYMES', 'full_finetune')
+    a64.load_state_dict(sd)
+    a64 = a64.double()
+    b = prod.FinetuneGNN(DEV, 'ENZYMES', 'full_finetune')
+    b.load_state_dict(sd)
+    for train in (False, True):
+        outs = {}
+        for name, m, mk, dt in (('f64', a64, oracle_batch, torch.float64), ('f32', a32, oracle_batch, torch.float32),
+                                ('gpu', b, lambda gr: product_batch(gr, DEV), torch.float32)):
+            m.train(train)
+            _zero_dropout(m)
+            for p_ in m.parameters():
+                p_.grad = None
+            with _NoDropout(prod, orc):
+                bt = mk(graphs)
+                x = bt.x.to(dt).clone().requires_grad_(True)
+                bt.x = x
+                y = m(bt)
+                w = torch.randn(y.shape, generator=torch.Generator().manual_seed(9)).to(y.device, dt)
+                (y * w).sum().backward()
+            grads = {k: p_.grad.detach().double().cpu() for k, p_ in m.named_parameters() if p_.grad is not None}
+            grads['x'] = x.grad.detach().double().cpu()
+            outs[name] = (y.detach().double().cpu(), grads)
+        fro = lambda u, v: float((u - v).norm() / v.norm().clamp(min=1e-300))       # noqa: E731
+        ref_y, ref_g = outs['f64']
+        floor_y = fro(outs['f32'][0], ref_y)
+        assert fro(outs['gpu'][0], ref_y) < max(2 * floor_y, ACT_TOL), (train, fro(outs['gpu'][0], ref_y), floor_y)
+        for k, v in ref_g.items():
+            if float(v.abs().max()) < 1e-9 or k.endswith('eps'):
+                continue                                        # analytically zero (bias feeding BatchNorm) / one cancelling dot
+            floor = fro(outs['f32'][1][k], v)
+            got = fro(outs['gpu'][1][k], v)
+            assert got < max(2 * floor, FRO_TOL), (train, k, got, floor)

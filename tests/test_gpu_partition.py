@@ -189,3 +189,38 @@ def _peer_worker(rank, world, port, out_dir):
 def test_world2_peer_halo_equals_dense(tmp_path):
     mp.spawn(_peer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(2))
+
+
+def _c4_worker(rank, world, port, out_dir):
+    """BASELINE configs[3] on NCCL: every rank runs gnnb200.pretrain.train_step on its own graphs with the flat gradient
+    all-reduce (mean); replicas start from the same seed, so after 3 steps every parameter and optimizer-visible buffer
+    must hold the same BITS on every rank (BatchNorm running statistics stay per replica: DDP semantics)."""
+    import importlib.util
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location('bench_for_c4_test', os.path.join(root, 'bench.py'))
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+        step, sampler = bench.build_c4_step(dev, rank, world)
+        start = torch.cat([p.detach().reshape(-1) for p in step.model.parameters()]).clone()
+        metrics = [step(sampler.draw()) for _ in range(3)]
+        flat = torch.cat([p.detach().reshape(-1) for p in step.model.parameters()])
+        assert torch.isfinite(flat).all() and all(torch.isfinite(torch.tensor(float(m['train/loss/total']))) for m in metrics)
+        assert not torch.equal(flat, start)                           # the optimizer moved the weights
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        for r in range(1, world):
+            assert torch.equal(both[0], both[r]), f'replica {r} diverged from replica 0'
+        open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_world2_c4_data_parallel_replicas_stay_identical(tmp_path):
+    mp.spawn(_c4_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(2))

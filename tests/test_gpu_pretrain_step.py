@@ -16,9 +16,7 @@ import gnnb200  # noqa: F401
 from gnnb200 import models, pretrain, synthetic, tasks as ptasks
 from gnnb200.gradient_surgery import GradientSurgery
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get('GNNB200_RUN_UNVERIFIED'),
-                                 reason='not yet run on a GPU (set GNNB200_RUN_UNVERIFIED=1)')]
+pytestmark = pytest.mark.gpu
 
 DOMAINS = ['MUTAG', 'ENZYMES']
 S5 = ['node_feat_mask', 'link_pred', 'node_contrast', 'graph_contrast', 'graph_prop', 'domain_adv']

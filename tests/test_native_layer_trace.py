@@ -118,14 +118,18 @@ def _layer_inputs(n, C, e, h_requires_grad, eps_requires_grad, strided_h):
     return h, eps, w1, b1, bn1, w2, b2, bn2, graph
 
 
-def _run(monkeypatch, native, training, drop_p, backward, **kw):
+def _run(monkeypatch, native, training, drop_p, backward, precision='tf32', **kw):
     rec = _Recorder(monkeypatch)
     monkeypatch.setattr(fused, 'NATIVE_LAYER', native)
     h, eps, w1, b1, bn1, w2, b2, bn2, graph = _layer_inputs(**kw)
     bn1.train(training)
     bn2.train(training)
+    if precision == 'tf32_fwd3':          # the weight split is cached per optimizer step: warm it so that neither trace holds it
+        ops.split_weight(w1), ops.split_weight(w2)
+        assert [n for n, _ in rec.trace] == ['gnnb200_split_tf32_f32'] * 2
+        rec.trace.clear()
     out = fused.GINLayerFn.apply(h, eps, w1, b1, bn1.weight, bn1.bias, w2, b2, bn2.weight, bn2.bias, graph, bn1, bn2,
-                                 training, drop_p, 1234567890123 if drop_p else 0, ops.PRECISIONS['tf32'])
+                                 training, drop_p, 1234567890123 if drop_p else 0, ops.PRECISIONS[precision])
     if backward:
         out.sum().backward()
     grads = [None if t.grad is None else tuple(t.grad.shape) for t in (h, eps, w1, b1, w2, b2, bn1.weight, bn1.bias,
@@ -143,18 +147,21 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize('precision,raw_hi', [('tf32', False), ('tf32_fwd3', False), ('tf32_fwd3', True)])
 @pytest.mark.parametrize('case', CASES, ids=[f'case{i}' for i in range(len(CASES))])
-def test_composite_makes_the_same_calls_as_the_python_path(monkeypatch, case):
-    want, grads_py, counts_py = _run(monkeypatch, False, **case)
-    got, grads_c, counts_c = _run(monkeypatch, True, **case)
+def test_composite_makes_the_same_calls_as_the_python_path(monkeypatch, case, precision, raw_hi):
+    monkeypatch.setattr(ops, 'X3W_RAW_HI', raw_hi)
+    want, grads_py, counts_py = _run(monkeypatch, False, precision=precision, **case)
+    got, grads_c, counts_c = _run(monkeypatch, True, precision=precision, **case)
     assert [n for n, _ in got] == [n for n, _ in want]
     for (name, a), (_, b) in zip(got, want):
         assert a == b, f'{name}:\n composite {a}\n python    {b}'
     assert grads_c == grads_py and counts_c == counts_py
     # the composite really replaced the per-kernel calls: the expected sequence for a training step
     if case['training'] and case['backward'] and case['h_requires_grad'] and case['eps_requires_grad']:
+        fwd_gemm = 'linear_x3w' if precision == 'tf32_fwd3' else 'gemm'
         assert [n[8:-4] for n, _ in got] == [
-            'aggregate', 'gemm', 'colstats', 'bn_finalize', 'bn_act_fwd', 'gemm', 'colstats', 'bn_finalize', 'bn_act_fwd',
+            'aggregate', fwd_gemm, 'colstats', 'bn_finalize', 'bn_act_fwd', fwd_gemm, 'colstats', 'bn_finalize', 'bn_act_fwd',
             'bn_act_bwd', 'gemm', 'gemm', 'bn_act_bwd', 'gemm', 'gemm', 'dot', 'aggregate']
 
 

@@ -31,12 +31,7 @@ def test_aggregation_full_c5_scale():
     check_aggregation_properties(forward, backward, dev, synthetic.C5_NODES, synthetic.C5_EDGES, 256)
 
 
-_unverified = pytest.mark.skipif(not __import__('os').environ.get('GNNB200_RUN_UNVERIFIED'),
-                                 reason='not yet run on a GPU (set GNNB200_RUN_UNVERIFIED=1)')
-
-
 @pytest.mark.gpu
-@_unverified
 @pytest.mark.parametrize('precision', ['tf32_strict', 'tf32x3_strict'])
 def test_gemm_full_c5_rows_exact_on_small_integers(precision):
     """The three GEMM layouts of a GIN layer at M (or K) = 2,449,029 rows.  Small integers are exact in tf32 and every
@@ -66,7 +61,6 @@ def test_gemm_full_c5_rows_exact_on_small_integers(precision):
 
 
 @pytest.mark.gpu
-@_unverified
 @pytest.mark.parametrize('cols', [256, 512])
 def test_batchnorm_full_c5_rows_against_torch(cols):
     """Fused BatchNorm+ReLU forward/backward over 2,449,029 rows against torch's own CUDA batch_norm + relu (fp32)."""
@@ -98,7 +92,6 @@ def test_batchnorm_full_c5_rows_against_torch(cols):
 
 
 @pytest.mark.gpu
-@_unverified
 def test_aggregation_full_c5_every_row_against_the_c_oracle():
     """Not a sample: the WHOLE [2,449,029 x 256] output of the forward aggregation at BASELINE config 5's size, bit for bit
     against the plain-C edge-order loop (oracle/c/oracle_c.c, one host thread, ~1 min), and the transposed pass likewise."""
