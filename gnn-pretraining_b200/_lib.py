@@ -56,6 +56,7 @@ SIGNATURES = {
     'gnnb200_linear_x3w_f32': [P, I64, P, P, P, I64, P, I64, I64, I64, I64, P, P, I64, c_int, c_int, P, P, P, SZP, P],
     'gnnb200_colstats_f32': [P, I64, I64, I64, P, P, P, SZP, P],
     'gnnb200_bn_finalize_f32': [P, P, I64, I64, c_float, c_float, P, P, P, P, P],
+    'gnnb200_bn_merge_finalize_f32': [P, I64, I64, c_float, c_float, P, P, P, P, P],
     'gnnb200_bn_act_fwd_f32': [P, I64, P, P, P, P, c_int, c_float, c_uint64, I64, I64, P, I64, P],
     'gnnb200_bn_act_bwd_f32': [P, I64, P, I64, P, P, P, P, c_int, c_float, c_uint64, c_int, c_int, I64, I64, I64, P, I64, P, P, P, SZP, P],
     'gnnb200_lp_features_f32': [P, I64, P, I64, I64, P, I64, P],

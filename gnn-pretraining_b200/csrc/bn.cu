@@ -44,6 +44,36 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   }
 }
 
+// Node-partitioned BatchNorm: every rank's (n, sum, centred m2) per column, all-gathered into [parts][3][cols], merged in
+// rank order with Chan's formula (same inputs in the same order on every rank => identical bits everywhere) and
+// finalised like bn_finalize_kernel — one launch instead of the ~15 elementwise launches of the torch expression.
+__global__ void bn_merge_finalize_kernel(const float* __restrict__ moments, int parts, float eps, float momentum, int cols,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float n = 0.f, sum = 0.f;
+  for (int r = 0; r < parts; ++r) {
+    n += moments[((int64_t)r * 3 + 0) * cols + c];
+    sum += moments[((int64_t)r * 3 + 1) * cols + c];
+  }
+  const float mu = sum / fmaxf(n, 1.f);
+  float m2 = 0.f;
+  for (int r = 0; r < parts; ++r) {
+    const float nr = moments[((int64_t)r * 3 + 0) * cols + c];
+    const float d = moments[((int64_t)r * 3 + 1) * cols + c] / fmaxf(nr, 1.f) - mu;
+    m2 += moments[((int64_t)r * 3 + 2) * cols + c] + nr * d * d;
+  }
+  const float var = m2 / fmaxf(n, 1.f);
+  mean[c] = mu;
+  invstd[c] = rsqrtf(var + eps);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+  if (running_var) {
+    const float unbiased = n > 1.f ? m2 / (n - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
 // One thread handles 4 consecutive columns of one row (cols % 4 == 0); grid-stride over rows*cols/4.
 template <bool DROP>
 __global__ void __launch_bounds__(256)
@@ -212,6 +242,19 @@ extern "C" int gnnb200_bn_finalize_f32(const float* sum, const float* m2, int64_
   if (!sum || !m2 || !mean || !invstd) return GNNB200_EINVAL;
   bn_finalize_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(sum, m2, (float)rows, eps, momentum, (int)cols,
                                                                         running_mean, running_var, mean, invstd);
+  GNNB200_LAUNCH_CHECK();
+  return GNNB200_OK;
+}
+
+extern "C" int gnnb200_bn_merge_finalize_f32(const float* moments, int64_t parts, int64_t cols, float eps, float momentum,
+                                             float* running_mean, float* running_var, float* mean, float* invstd,
+                                             gnnb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (parts <= 0 || cols < 0 || parts > 4096) return GNNB200_EINVAL;
+  if (cols == 0) return GNNB200_OK;
+  if (!moments || !mean || !invstd) return GNNB200_EINVAL;
+  bn_merge_finalize_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(moments, (int)parts, eps, momentum, (int)cols,
+                                                                              running_mean, running_var, mean, invstd);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }

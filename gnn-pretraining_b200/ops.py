@@ -70,6 +70,31 @@ def _ld(t: Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
 
 
+def _tma_rows(t: Tensor) -> Tensor:
+    """`t` with a row pitch TMA can address (a multiple of 16 bytes, 16-byte aligned base): the tensor itself when it
+    already is, else the [rows, cols] view of a zero-padded copy with leading dimension ceil4(cols) — same logical shape,
+    so the tensor-core GEMM covers feature widths such as 1433 / 3703 / 21 / 7 / 37 (src/data/data_setup.py:31-41) instead
+    of dropping to the FFMA kernel.  The copy is cached on the tensor object until it is modified in place (dataset
+    features and weights are re-used every step)."""
+    if t.size(1) % 4 == 0 and _ld(t) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    if _ld(t) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t                                           # ragged width on an aligned pitch: TMA clips the box
+    key = (t._version, t.data_ptr(), tuple(t.shape))
+    cached = getattr(t, '_gnnb200_tma_rows', None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    src = t.detach()
+    pad = torch.zeros(src.size(0), (src.size(1) + 3) // 4 * 4, dtype=src.dtype, device=src.device)
+    view = pad[:, : src.size(1)]
+    view.copy_(src)
+    try:
+        t._gnnb200_tma_rows = (key, view)
+    except AttributeError:
+        pass
+    return view
+
+
 # Own-kernel launches per entry-point call (library kernels such as CUB's sort are not counted).
 KERNELS_PER_CALL = {
     'gnnb200_csr_build_i64': 2, 'gnnb200_segment_ptr_i64': 1, 'gnnb200_coalesce_i64': 3,
@@ -77,7 +102,7 @@ KERNELS_PER_CALL = {
     'gnnb200_segment_pool_bwd_f32': 1, 'gnnb200_rows_gather_f32': 1, 'gnnb200_rows_scatter_f32': 1,
     'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_linear_x3w_f32': 1, 'gnnb200_split_tf32_f32': 1,
     'gnnb200_colstats_f32': 2,
-    'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
+    'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_merge_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
     'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,
@@ -543,8 +568,9 @@ rows_scatter.register_autograd(_rs_backward, setup_context=_rs_setup)
 # plain tf32 in dX / dW alone stays at 3e-3 .. 6e-3.
 PRECISIONS = {'f32': L.GEMM_F32, 'tf32': L.GEMM_AUTO, 'tf32_strict': L.GEMM_TF32,
               'tf32x3': L.GEMM_AUTO_X3, 'tf32x3_strict': L.GEMM_TF32X3, 'tf32_fwd3': L.GEMM_AUTO_FWD3}
+_PAD_PRECISIONS = (L.GEMM_AUTO, L.GEMM_AUTO_X3, L.GEMM_AUTO_FWD3)     # the non-strict tensor-core modes
 # raw weights as the hi operand (kind::tf32 reads only the upper 19 bits of a word): the splitter warps then only write lo(A)
-X3W_RAW_HI = os.environ.get('GNNB200_X3W_RAW_HI', '0') == '1'
+X3W_RAW_HI = os.environ.get('GNNB200_X3W_RAW_HI', '1') == '1'
 
 
 def split_weight(w: Tensor) -> Tuple[Optional[Tensor], Tensor]:
@@ -555,8 +581,14 @@ def split_weight(w: Tensor) -> Tuple[Optional[Tensor], Tensor]:
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]
     src = w.detach()
-    hi, lo = torch.empty_like(src), torch.empty_like(src)
-    L.check(_invoke('gnnb200_split_tf32_f32', _ptr(src), src.numel(), _ptr(hi), _ptr(lo), _stream(src)), 'split_tf32')
+    rows, pitch = src.size(0), _ld(src)
+    if src.is_contiguous():
+        hi, lo, count = torch.empty_like(src), torch.empty_like(src), src.numel()
+    else:                                                   # a _tma_rows view: split the whole padded buffer, keep its pitch
+        hi = torch.empty(rows, pitch, dtype=src.dtype, device=src.device)[:, : src.size(1)]
+        lo = torch.empty(rows, pitch, dtype=src.dtype, device=src.device)[:, : src.size(1)]
+        count = rows * pitch
+    L.check(_invoke('gnnb200_split_tf32_f32', _ptr(src), count, _ptr(hi), _ptr(lo), _stream(src)), 'split_tf32')
     if X3W_RAW_HI:
         hi = None
     w._gnnb200_split = (key, hi, lo)
@@ -575,7 +607,9 @@ def _linear_fwd_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor], relu: boo
     N = weight.size(0)
     if K != weight.size(1):
         raise L.Gnnb200Error(f'linear inner dimensions differ: {K} vs {weight.size(1)}')
-    if not weight.is_contiguous():
+    if N % 4 == 0 and N >= 8 and M > 0 and K > 0:
+        x, weight = _tma_rows(x), _tma_rows(weight)        # K % 4 != 0 (1433, 3703, 21, 7, 37): padded pitch, same logical K
+    elif not weight.is_contiguous():
         weight = weight.contiguous()
     hi, lo = split_weight(weight)
     y = torch.empty(M, N, dtype=torch.float32, device=x.device)
@@ -590,10 +624,10 @@ def _linear_fwd_raw(x: Tensor, weight: Tensor, bias: Optional[Tensor], relu: boo
         csum = torch.empty(N, dtype=torch.float32, device=x.device)
         cm2 = torch.empty(N, dtype=torch.float32, device=x.device)
     _call_ws('gnnb200_linear_x3w_f32', 'linear (3xTF32, pre-split weights)', x.device, _ptr(x), _ld(x), _ptr(weight),
-             _ptr(hi), _ptr(lo), K, _ptr(y), _ld(y), M, N, K, _ptr(bias), _ptr(residual),
+             _ptr(hi), _ptr(lo), _ld(weight), _ptr(y), _ld(y), M, N, K, _ptr(bias), _ptr(residual),
              _ld(residual) if residual is not None else 0, L.EPI_RELU if relu else L.EPI_NONE, int(X3W_RAW_HI), _ptr(csum),
              _ptr(cm2), stream=_stream(x),
-             key=(M, N, K, _ld(x) % 4, residual is None or _ld(residual) % 4 == 0, x.data_ptr() % 16, want_stats))
+             key=(M, N, K, _ld(x) % 4, _ld(weight) % 4, residual is None or _ld(residual) % 4 == 0, x.data_ptr() % 16, want_stats))
     return (y, csum, cm2) if want_stats else y
 
 
@@ -606,6 +640,8 @@ def _gemm_raw(a: Tensor, transa: bool, b: Tensor, transb: bool, bias: Optional[T
     Kb, N = (b.size(1), b.size(0)) if transb else (b.size(0), b.size(1))
     if K != Kb:
         raise L.Gnnb200Error(f'gemm inner dimensions differ: {K} vs {Kb}')
+    if precision in _PAD_PRECISIONS and N % 4 == 0 and N >= 8 and M > 0 and K > 0:
+        a, b = _tma_rows(a), _tma_rows(b)                  # e.g. x [N, 1433]: pitch 1436, logical width unchanged
     c = torch.empty(M, N, dtype=torch.float32, device=a.device)
     if bias is not None:
         bias = bias.contiguous()
@@ -704,7 +740,11 @@ def _lin_backward(ctx, g):
     if ctx.needs_input_grad[0]:
         gx = gemm(g, False, weight, False, None, False, ctx.precision)      # [M,out] x [out,in]
     if ctx.needs_input_grad[1]:
-        gw = gemm(g, True, x, False, None, False, ctx.precision)            # [out,M] x [M,in]
+        if x.size(1) % 4 != 0 and g.size(1) % 4 == 0 and g.size(1) >= 8 and ctx.precision in _PAD_PRECISIONS:
+            # in-features not a multiple of 4 (encoders): the tensor-core kernel needs N % 4 == 0, so form dW^T = x^T g
+            gw = gemm(x, True, g, False, None, False, ctx.precision).t().contiguous()
+        else:
+            gw = gemm(g, True, x, False, None, False, ctx.precision)        # [out,M] x [M,in]
     if ctx.has_bias and ctx.needs_input_grad[2]:
         gb = torch.zeros(g.size(1), dtype=g.dtype, device=g.device) if ctx.zero_bias_grad else colsum(g)
     gres = g if (ctx.has_residual and ctx.needs_input_grad[4]) else None

@@ -391,6 +391,24 @@ def synced_batch_stats(x_local: Tensor, graph_rows_total: int, group, running_me
                        ) -> Tuple[Tensor, Tensor]:
     """Global (mean, invstd) of a row-partitioned activation: per-rank (n, sum, m2) gathered and merged with
     Chan's formula in rank order; running buffers updated from the global moments (torch's rule)."""
+    cols = x_local.size(1)
+    if local_stats is None and ops.on_device(x_local) and x_local.is_cuda:
+        # three launches + one collective: the column statistics land in rows 1-2 of the send buffer, row 0 is the row
+        # count; after the all-gather one kernel merges the ranks' moments and finalises (gnnb200_bn_merge_finalize_f32)
+        world = dist.get_world_size(group)
+        x2 = ops._rowmajor(x_local.detach())
+        mine = torch.empty(3, cols, dtype=torch.float32, device=x_local.device)
+        mine[0].fill_(float(x_local.size(0)))
+        ops._call_ws('gnnb200_colstats_f32', 'bn colstats', x2.device, x2.data_ptr(), ops._ld(x2), x2.size(0), cols,
+                     mine[1].data_ptr(), mine[2].data_ptr(), stream=ops._stream(x2), key=(x2.size(0), cols))
+        everyone = torch.empty(world * 3, cols, dtype=torch.float32, device=x_local.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        mean_out = torch.empty(cols, dtype=torch.float32, device=x_local.device)
+        invstd = torch.empty(cols, dtype=torch.float32, device=x_local.device)
+        L.check(ops._invoke('gnnb200_bn_merge_finalize_f32', everyone.data_ptr(), world, cols, eps, momentum,
+                            ops._ptr(running_mean), ops._ptr(running_var), mean_out.data_ptr(), invstd.data_ptr(),
+                            ops._stream(x2)), 'bn_merge_finalize')
+        return mean_out, invstd
     s, m2 = local_stats if local_stats is not None else ops.colstats(x_local.detach())
     _, gsum, m2_tot = merge_moments(gather_moments(x_local.size(0), s, m2, group))
     mean_out = torch.empty_like(s)

@@ -198,6 +198,11 @@ int gnnb200_colstats_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols
 int gnnb200_bn_finalize_f32(const float* sum, const float* m2, int64_t rows, int64_t cols, float eps,
                             float momentum, float* running_mean, float* running_var, float* mean,
                             float* invstd, gnnb200_stream_t stream);
+/* Node-partitioned batches (BASELINE config 5): moments [parts][3][cols] = every rank's (row count, column sums, centred
+ * second moments) after an all-gather; merged in rank order (Chan) and finalised as above in one launch. */
+int gnnb200_bn_merge_finalize_f32(const float* moments, int64_t parts, int64_t cols, float eps, float momentum,
+                                  float* running_mean, float* running_var, float* mean, float* invstd,
+                                  gnnb200_stream_t stream);
 int gnnb200_bn_act_fwd_f32(const float* x, int64_t ldx, const float* mean, const float* invstd,
                            const float* gamma, const float* beta, int relu, float drop_p, uint64_t seed,
                            int64_t rows, int64_t cols, float* y, int64_t ldy, gnnb200_stream_t stream);

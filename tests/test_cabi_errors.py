@@ -86,6 +86,8 @@ BAD = [
     # ---- BatchNorm ----
     ('gnnb200_bn_finalize_f32', (D, D, 0, 256, 1e-5, 0.1, None, None, D, D, None), L.EINVAL),  # rows must be > 0
     ('gnnb200_bn_finalize_f32', (None, D, 10, 256, 1e-5, 0.1, None, None, D, D, None), L.EINVAL),
+    ('gnnb200_bn_merge_finalize_f32', (D, 0, 256, 1e-5, 0.1, None, None, D, D, None), L.EINVAL),               # no parts
+    ('gnnb200_bn_merge_finalize_f32', (None, 8, 256, 1e-5, 0.1, None, None, D, D, None), L.EINVAL),
     ('gnnb200_bn_act_fwd_f32', (D, 256, D, D, D, D, 1, 1.0, 0, 10, 256, D, 256, None), L.EINVAL),            # p must be < 1
     ('gnnb200_bn_act_fwd_f32', (D, 256, D, D, D, D, 1, -0.1, 0, 10, 256, D, 256, None), L.EINVAL),
     ('gnnb200_bn_act_fwd_f32', (D, 256, None, D, D, D, 1, 0.0, 0, 10, 256, D, 256, None), L.EINVAL),

@@ -99,3 +99,35 @@ def test_fused_dropout_statistics_and_backward_mask():
     torch.manual_seed(8)
     y3 = mine(x, drop_p=0.2)
     assert not torch.equal(y3, y2)                              # a new seed gives a new mask
+
+
+@pytest.mark.parametrize('parts,cols', [(1, 256), (2, 512), (8, 256), (3, 100)])
+def test_merge_finalize_kernel_equals_the_moments_of_the_whole(parts, cols):
+    """The node-partitioned BatchNorm statistics: per-shard (n, sum, m2) merged by gnnb200_bn_merge_finalize_f32 must give
+    the mean / invstd / running buffers of the unpartitioned rows (fp32 class), with shards of different sizes."""
+    from gnnb200 import _lib as L, ops, partition
+    g = torch.Generator().manual_seed(parts * 1000 + cols)
+    sizes = [int(v) for v in torch.randint(1, 4000, (parts,), generator=g)]
+    x = torch.randn(sum(sizes), cols, generator=g) * 3 + 20.0
+    moments = []
+    lo = 0
+    for n in sizes:
+        xs = x[lo:lo + n].to(DEV)
+        lo += n
+        if cols % 4 == 0:
+            s, m2 = ops.colstats(xs)
+        else:
+            s, m2 = xs.sum(0), ((xs - xs.mean(0)) ** 2).sum(0)
+        moments.append(torch.stack([torch.full_like(s, float(n)), s, m2]))
+    moments = torch.stack(moments).contiguous()                      # [P, 3, C]
+    rm, rv = torch.zeros(cols, device=DEV), torch.ones(cols, device=DEV)
+    mean, invstd = torch.empty(cols, device=DEV), torch.empty(cols, device=DEV)
+    L.check(ops._invoke('gnnb200_bn_merge_finalize_f32', moments.data_ptr(), parts, cols, 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(),
+                        mean.data_ptr(), invstd.data_ptr(), ops._stream(moments)), 'merge')
+    xd = x.double()
+    assert _rel(mean, xd.mean(0)) < 1e-6
+    assert _rel(invstd, 1.0 / torch.sqrt(xd.var(0, unbiased=False) + 1e-5)) < 1e-5
+    assert _rel(rm, 0.1 * xd.mean(0)) < 1e-6
+    assert _rel(rv, 0.9 + 0.1 * xd.var(0, unbiased=True)) < 1e-5
+    n_tot, s_tot, m2_tot = partition.merge_moments(moments)             # the torch expression it replaces
+    assert _rel(mean, (s_tot / n_tot).double().cpu()) < 1e-6 and _rel(invstd, torch.rsqrt(m2_tot / n_tot + 1e-5).double().cpu()) < 1e-5

@@ -144,12 +144,54 @@ def test_linear_autograd_tf32():
 
 
 def test_tf32_falls_back_to_ffma_only_for_illegal_layouts():
+    """Row pitches that are not a multiple of 16 bytes (feature widths 1433, 3703, 21, 7, 37): the strict mode refuses them,
+    the module-level modes re-pitch the operand once (ops._tma_rows, cached on the tensor) and stay on the tensor cores;
+    only outputs the kernel cannot store 128 bits at a time (N % 4 != 0, N = 1) take the FFMA kernel."""
     a = torch.randn(50, 1433, device=DEV)      # row pitch 1433 floats: not 16-byte aligned
     w = torch.randn(256, 1433, device=DEV)
     with pytest.raises(Exception):
         ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32_strict'])
+    want = a.double().cpu() @ w.double().cpu().t()
+    ops.reset_counters()
     got = ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32'])
-    assert _rel(got, a.double().cpu() @ w.double().cpu().t()) < TOL_F32
+    err = _rel(got, want)
+    assert 1e-6 < err < 5e-3, err               # tf32 rounding is visible: the tensor-core kernel ran
+    assert ops._tma_rows(a) is ops._tma_rows(a) and ops._tma_rows(a).stride(0) == 1436          # cached, re-pitched
+    assert _rel(ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32x3']), want) < TOL_F32
+    a.add_(1.0)                                 # an in-place edit invalidates the cached copy
+    assert _rel(ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32x3']), a.double().cpu() @ w.double().cpu().t()) < TOL_F32
+    w1 = torch.randn(1, 256, device=DEV)        # N = 1 (the link decoder's last layer): FFMA, fp32 class
+    x = torch.randn(300, 256, device=DEV)
+    assert _rel(ops.gemm(x, False, w1, True, None, False, ops.PRECISIONS['tf32']), x.double().cpu() @ w1.double().cpu().t()) < TOL_F32
+
+
+@pytest.mark.parametrize('rows,fin,fout', [(2708, 1433, 256), (3327, 3703, 256), (4340, 21, 256), (600, 7, 256), (900, 37, 256)])
+def test_encoder_widths_run_on_the_tensor_cores(rows, fin, fout):
+    """InputEncoder's Linear for every dataset's feature width (src/models/gnn.py:13, src/data/data_setup.py:31-41) under the
+    default precision: forward in the fp32 class, dW through the transposed product x^T g (the kernel stores N % 4 == 0)."""
+    g = torch.Generator().manual_seed(rows + fin)
+    ref = torch.nn.Linear(fin, fout)
+    lin = Linear(fin, fout)
+    lin.precision = 'tf32_fwd3'
+    lin.load_state_dict(ref.state_dict())
+    lin = lin.to(DEV)
+    x = torch.randn(rows, fin, generator=g)
+    go = torch.randn(rows, fout, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).backward(go)
+    xd = x.to(DEV)
+    ops.reset_counters()
+    y = lin(xd)
+    y.backward(go.to(DEV))
+    assert 'gnnb200_linear_x3w_f32' in ops.call_counts()
+    assert _rel(y, ref(x).detach()) < TOL_F32
+    assert lin.weight.grad.shape == ref.weight.grad.shape and lin.weight.grad.is_contiguous()
+    err = _rel(lin.weight.grad, ref.weight.grad)
+    assert 1e-7 < err < 5e-3, err               # tf32 noise: the weight gradient came from the tensor-core kernel
+    assert _rel(lin.bias.grad, ref.bias.grad) < 2e-5
+    xg = x.to(DEV).requires_grad_(True)          # input gradient (not needed by the encoders, but part of the op)
+    lin(xg).backward(go.to(DEV))
+    assert _rel(xg.grad, xr.grad) < 5e-3
 
 
 @pytest.mark.parametrize('prec', ['f32', 'tf32'])
