@@ -152,9 +152,10 @@ def step_fn(model, opt, x, edge_index):
 def partition_selfcheck(prod, dev, rank, world, halo):
     """Parity of the path that is about to be timed, on the hardware it is timed on: a 200 k-node / 5 M-edge graph of the
     same generator, same seeded model on every rank, dropout off.  All ranks run one node-partitioned forward + backward
-    (+ the flat gradient all-reduce); rank 0 also runs the single-device path and compares: the first layer's
-    aggregation output (pure gather: must be bit-identical), the backbone output (BatchNorm moments are merged in another
-    order across ranks: fp32 rounding), the loss, and the Frobenius error over all parameter gradients.  N = 1 reports
+    (+ the flat gradient all-reduce); rank 0 also runs the single-device path and compares: the aggregation of a fixed
+    [n, 256] matrix, forward and transposed (pure gather in edge order: must be bit-identical), the backbone output
+    (BatchNorm moments are merged in another order across ranks: fp32 rounding), the loss, and the Frobenius error over
+    all parameter gradients.  N = 1 reports
     the single-device loss of the same graph and seed, so the lines of a scaling run can be read side by side."""
     import torch.distributed as dist
     from gnnb200 import partition
@@ -174,23 +175,28 @@ def partition_selfcheck(prod, dev, rank, world, halo):
         ref = None
         if rank == 0:
             m1 = fresh()
+            from gnnb200 import _lib as L_, ops as ops_
+            from gnnb200.graph import graph_of
             h0 = m1['input_encoder'](x)
-            z1 = m1['gnn_backbone'].layers[0].gin_conv.aggregate(h0, ei)
             h1 = m1['gnn_backbone'](h0, ei)
             loss1 = (h1 * w).sum()
             loss1.backward()
-            ref = (z1.detach(), h1.detach(), float(loss1), torch.cat([p.grad.reshape(-1) for p in m1.parameters()]))
+            g1, eps1 = graph_of(ei, n), torch.tensor([0.25], device=dev)
+            z1 = torch.cat([ops_._aggregate_raw(w, g1.rowptr, g1.col, L_.AGG_SUM, w, eps1, None),
+                            ops_._aggregate_raw(w, g1.rowptr_t, g1.col_t, L_.AGG_SUM, w, eps1, None)], dim=1)
+            ref = (z1, h1.detach(), float(loss1), torch.cat([p.grad.reshape(-1) for p in m1.parameters()]))
             out['loss_single_device'] = ref[2]
         if world > 1:
             m = fresh()
             graph = partition.PartitionedGraph(ei, n, rank, world, halo=halo)
             with partition.partition_scope(graph):
                 h0 = m['input_encoder'](x[graph.lo:graph.hi])
-                z = m['gnn_backbone'].layers[0].gin_conv.aggregate(h0, graph)
                 h = m['gnn_backbone'](h0, graph)
                 loss = (h * w[graph.lo:graph.hi]).sum()
                 loss.backward()
             partition.allreduce_gradients(m)
+            w_local, eps1 = w[graph.lo:graph.hi].contiguous(), torch.tensor([0.25], device=dev)
+            z = torch.cat([graph.aggregate(w_local, eps1, False), graph.aggregate(w_local, eps1, True)], dim=1)
             total = loss.detach().clone()
             dist.all_reduce(total)
 

@@ -67,6 +67,15 @@ SIGNATURES = {
     'gnnb200_normalize_rows_bwd_f32': [P, P, I64, P, I64, I64, P, I64, P],
     'gnnb200_ntxent_sim_fwd_f32': [P, I64, I64, c_float, P, P, P, P],
     'gnnb200_ntxent_sim_bwd_f32': [P, I64, I64, c_float, P, P, P],
+    'gnnb200_act_dropout_fwd_f32': [P, I64, c_int, c_float, c_uint64, P, P],
+    'gnnb200_act_dropout_bwd_f32': [P, P, I64, c_float, P, P],
+    'gnnb200_scale_f32': [P, I64, c_float, P, P],
+    'gnnb200_sqdiff_sum_f32': [P, P, I64, P, P, SZP, P],
+    'gnnb200_sqdiff_bwd_f32': [P, P, P, I64, P, P],
+    'gnnb200_sigmoid_bce_fwd_f32': [P, P, I64, P, P, P, SZP, P],
+    'gnnb200_sigmoid_bce_bwd_f32': [P, P, P, I64, P, P],
+    'gnnb200_ce_sum_fwd_f32': [P, I64, P, I64, I64, P, P, P, SZP, P],
+    'gnnb200_ce_bwd_f32': [P, I64, P, P, P, I64, I64, P, I64, P],
     'gnnb200_pcgrad_f32': [P, P, I64, I64, P, I64, P, P, P, P, P, P, P],
     'gnnb200_aggregate_peer_f32': [P, c_int, I64, P, P, I64, I64, P, I64, P, P, I64, P],
     'gnnb200_peer_publish_f32': [P, I64, I64, I64, P, I64, P],

@@ -91,6 +91,8 @@ def _classification_outputs(logits: Tensor, targets: Tensor, domain_name: str) -
     """finetune.py:150-160 / :171-181: binary domains train the positive-class logit with BCE-with-logits."""
     if NUM_CLASSES[domain_name] == 2:
         loss = F.binary_cross_entropy_with_logits(logits[:, 1], targets.float())
+    elif ops.on_device(logits) and logits.dim() == 2 and logits.size(0) > 0:
+        loss = ops.cross_entropy_sum(logits, targets)[0] / logits.size(0)      # F.cross_entropy (mean) in one launch
     else:
         loss = F.cross_entropy(logits, targets)
     return loss, targets, torch.argmax(logits, dim=1), F.softmax(logits, dim=1)

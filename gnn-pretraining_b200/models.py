@@ -105,24 +105,13 @@ class GINBackbone(nn.Module):
         return h
 
 
-class GradientReversalFunction(torch.autograd.Function):
-    """reference src/models/heads.py:16-24."""
-
-    @staticmethod
-    def forward(ctx, x, lambda_val):
-        ctx.lambda_val = lambda_val
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, grad_output):
-        return grad_output.neg() * ctx.lambda_val, None
-
-
 class GradientReversalLayer(nn.Module):
-    """reference src/models/heads.py:27-32."""
+    """reference src/models/heads.py:16-32: identity forward, gradient times -lambda backward (one scale kernel)."""
 
     def forward(self, x, lambda_val):
-        return GradientReversalFunction.apply(x, lambda_val)
+        if not ops.on_device(x):
+            raise ops.L.Gnnb200Error('gnnb200 modules run on CUDA tensors only (no CPU fallback)')
+        return ops.gradient_reversal(x, lambda_val)
 
 
 class MLPHead(nn.Module):
@@ -139,7 +128,23 @@ class MLPHead(nn.Module):
         self.mlp = nn.Sequential(*stack)
 
     def forward(self, x: Tensor) -> Tensor:
-        return self.mlp(x)
+        # same modules / state-dict keys as the reference's nn.Sequential; executed as one fused step per hidden layer:
+        # Linear (+ ReLU in the GEMM epilogue) (+ one ReLU/dropout launch in training mode) instead of three eager kernels
+        mods = list(self.mlp)
+        if x.dim() != 2 or not ops.on_device(x):
+            return self.mlp(x)
+        i = 0
+        while i < len(mods):
+            lin = mods[i]
+            if i + 2 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and isinstance(mods[i + 2], nn.Dropout):
+                p = float(mods[i + 2].p) if self.training else 0.0
+                prec = ops.PRECISIONS[lin.precision or _gnn.default_precision()]
+                x = ops.linear_act(x, lin.weight, lin.bias, prec, p, _gnn._dropout_seed() if p > 0.0 else 0)
+                i += 3
+            else:
+                x = lin(x)
+                i += 1
+        return x
 
 
 class MLPLinkPredictor(nn.Module):
@@ -150,9 +155,16 @@ class MLPLinkPredictor(nn.Module):
         super().__init__()
         self.predictor = MLPHead([3 * hidden_dim, hidden_dim, 1])
 
+    def logits(self, h: Tensor, edge_index: Tensor) -> Tensor:
+        return self.predictor(ops.lp_features(h, edge_index)).squeeze(-1)
+
     def forward(self, h: Tensor, edge_index: Tensor) -> Tensor:
-        feats = ops.lp_features(h, edge_index)
-        return torch.sigmoid(self.predictor(feats).squeeze(-1))
+        return torch.sigmoid(self.logits(h, edge_index))
+
+    def loss(self, h: Tensor, edge_index: Tensor, labels: Tensor):
+        """(probs, F.binary_cross_entropy(probs, labels, reduction='sum')): sigmoid and the loss sum in one launch
+        (reference src/models/heads.py:67 + src/pretrain/tasks.py:120)."""
+        return ops.sigmoid_bce_sum(self.logits(h, edge_index), labels)
 
 
 class DomainClassifierHead(nn.Module):

@@ -103,6 +103,9 @@ KERNELS_PER_CALL = {
     'gnnb200_rows_gather_bwd_f32': 1, 'gnnb200_gemm_f32': 1, 'gnnb200_linear_x3w_f32': 1, 'gnnb200_split_tf32_f32': 1,
     'gnnb200_colstats_f32': 2,
     'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_merge_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
+    'gnnb200_act_dropout_fwd_f32': 1, 'gnnb200_act_dropout_bwd_f32': 1, 'gnnb200_scale_f32': 1, 'gnnb200_sqdiff_sum_f32': 1,
+    'gnnb200_sqdiff_bwd_f32': 1, 'gnnb200_sigmoid_bce_fwd_f32': 1, 'gnnb200_sigmoid_bce_bwd_f32': 1, 'gnnb200_ce_sum_fwd_f32': 1,
+    'gnnb200_ce_bwd_f32': 1,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
     'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,
@@ -939,6 +942,179 @@ def _bn_backward(ctx, gy):
 
 
 bn_act.register_autograd(_bn_backward, setup_context=_bn_setup)
+
+
+# ---------------------------------------------------------------------------------------------
+# head tails and loss sums (csrc/heads.cu): one launch forward, one backward
+# ---------------------------------------------------------------------------------------------
+class _LinearAct(torch.autograd.Function):
+    """y = dropout(relu(x W^T + b)): the hidden layers of MLPHead (reference src/models/heads.py:41-45).  Without dropout
+    the ReLU runs in the GEMM epilogue (one launch); with it, GEMM + one ReLU/dropout launch.  The backward recovers the
+    kept-and-positive mask from y (no second Philox pass), then the two GEMMs of the Linear."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int, drop_p: float, seed: int):
+        if drop_p > 0.0:
+            a = _linear_fwd_raw(x, weight, bias, False, precision)
+            y = torch.empty_like(a)
+            L.check(_invoke('gnnb200_act_dropout_fwd_f32', _ptr(a), a.numel(), 1, drop_p, seed, _ptr(y), _stream(a)),
+                    'act_dropout_fwd')
+        else:
+            y = _linear_fwd_raw(x, weight, bias, True, precision)
+        ctx.cfg = (precision, drop_p, bias is not None)
+        ctx.save_for_backward(x, weight, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        x, weight, y = ctx.saved_tensors
+        precision, drop_p, has_bias = ctx.cfg
+        g = g.contiguous()
+        ga = torch.empty_like(y)
+        L.check(_invoke('gnnb200_act_dropout_bwd_f32', _ptr(g), _ptr(y), y.numel(), drop_p, _ptr(ga), _stream(y)),
+                'act_dropout_bwd')
+        gx = gemm(ga, False, weight, False, None, False, precision) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            if x.size(1) % 4 != 0 and ga.size(1) % 4 == 0 and ga.size(1) >= 8 and precision in _PAD_PRECISIONS:
+                gw = gemm(x, True, ga, False, None, False, precision).t().contiguous()
+            else:
+                gw = gemm(ga, True, x, False, None, False, precision)
+        gb = colsum(ga) if has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None, None
+
+
+def linear_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], precision: int, drop_p: float, seed: int) -> Tensor:
+    return _LinearAct.apply(x, weight, bias, precision, drop_p, seed)
+
+
+class _ScaleGrad(torch.autograd.Function):
+    """Gradient reversal (reference src/models/heads.py:16-24): identity forward, grad * (-lambda) backward in one launch."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, lambda_val: float):
+        ctx.alpha = -float(lambda_val)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        L.check(_invoke('gnnb200_scale_f32', _ptr(g), g.numel(), ctx.alpha, _ptr(out), _stream(g)), 'scale')
+        return out, None
+
+
+def gradient_reversal(x: Tensor, lambda_val: float) -> Tensor:
+    return _ScaleGrad.apply(x, lambda_val)
+
+
+@_op('mse_sum')
+def mse_sum(pred: Tensor, target: Tensor) -> Tensor:
+    """sum((pred - target)^2) as a 0-d tensor = F.mse_loss(pred, target, reduction='sum'); gradient for `pred` only."""
+    _need_cuda(pred, target)
+    if pred.shape != target.shape:
+        raise L.Gnnb200Error(f'mse_sum: shapes differ: {tuple(pred.shape)} vs {tuple(target.shape)}')
+    a, b = pred.contiguous(), target.contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    _call_ws('gnnb200_sqdiff_sum_f32', 'mse_sum', a.device, _ptr(a), _ptr(b), a.numel(), _ptr(out), stream=_stream(a), key=())
+    return out.view(())
+
+
+@mse_sum.register_fake
+def _(pred, target):
+    return pred.new_empty(())
+
+
+def _mse_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _mse_backward(ctx, g):
+    pred, target = ctx.saved_tensors
+    a, b = pred.contiguous(), target.contiguous()
+    ga = torch.empty_like(a)
+    L.check(_invoke('gnnb200_sqdiff_bwd_f32', _ptr(a), _ptr(b), _ptr(g.contiguous().view(1)), a.numel(), _ptr(ga), _stream(a)),
+            'mse_sum backward')
+    return ga.view_as(pred), None
+
+
+mse_sum.register_autograd(_mse_backward, setup_context=_mse_setup)
+
+
+@_op('sigmoid_bce_sum')
+def sigmoid_bce_sum(logits: Tensor, labels: Tensor) -> Tuple[Tensor, Tensor]:
+    """(probs = sigmoid(logits), loss = F.binary_cross_entropy(probs, labels, reduction='sum') as a 0-d tensor): the tail
+    of the link-prediction task (reference src/models/heads.py:67 + src/pretrain/tasks.py:120) in one launch."""
+    _need_cuda(logits, labels)
+    z, t = logits.contiguous().view(-1), labels.contiguous().view(-1)
+    if z.numel() != t.numel() or t.dtype != torch.float32:
+        raise L.Gnnb200Error('sigmoid_bce_sum: logits and float32 labels of the same size')
+    probs = torch.empty_like(z)
+    loss = torch.empty(1, dtype=torch.float32, device=z.device)
+    _call_ws('gnnb200_sigmoid_bce_fwd_f32', 'sigmoid_bce', z.device, _ptr(z), _ptr(t), z.numel(), _ptr(probs), _ptr(loss),
+             stream=_stream(z), key=())
+    return probs.view_as(logits), loss.view(())
+
+
+@sigmoid_bce_sum.register_fake
+def _(logits, labels):
+    return torch.empty_like(logits), logits.new_empty(())
+
+
+def _bce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[0], inputs[1])
+
+
+def _bce_backward(ctx, g_probs, g_loss):
+    probs, labels = ctx.saved_tensors
+    if g_loss is None:
+        g_loss = torch.zeros((), dtype=torch.float32, device=probs.device)
+    p, t = probs.contiguous().view(-1), labels.contiguous().view(-1)
+    gz = torch.empty_like(p)
+    L.check(_invoke('gnnb200_sigmoid_bce_bwd_f32', _ptr(p), _ptr(t), _ptr(g_loss.contiguous().view(1)), p.numel(), _ptr(gz),
+                    _stream(p)), 'sigmoid_bce backward')
+    return gz.view_as(probs), None        # (probs is an output for metrics only: no gradient flows through it here)
+
+
+sigmoid_bce_sum.register_autograd(_bce_backward, setup_context=_bce_setup)
+
+
+@_op('cross_entropy_sum')
+def cross_entropy_sum(logits: Tensor, target: Tensor) -> Tuple[Tensor, Tensor]:
+    """(loss = F.cross_entropy(logits, target, reduction='sum') as a 0-d tensor, lse [rows])."""
+    _need_cuda(logits, target)
+    z = _rowmajor(logits)
+    t = target.contiguous()
+    if t.dtype != torch.int64 or t.numel() != z.size(0):
+        raise L.Gnnb200Error('cross_entropy_sum: int64 class indices, one per row')
+    lse = torch.empty(z.size(0), dtype=torch.float32, device=z.device)
+    loss = torch.empty(1, dtype=torch.float32, device=z.device)
+    _call_ws('gnnb200_ce_sum_fwd_f32', 'cross_entropy_sum', z.device, _ptr(z), _ld(z), _ptr(t), z.size(0), z.size(1), _ptr(lse),
+             _ptr(loss), stream=_stream(z), key=())
+    return loss.view(()), lse
+
+
+@cross_entropy_sum.register_fake
+def _(logits, target):
+    return logits.new_empty(()), logits.new_empty(logits.size(0))
+
+
+def _ce_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], output[1])
+
+
+def _ce_backward(ctx, g_loss, g_lse):
+    logits, target, lse = ctx.saved_tensors
+    if g_loss is None:
+        g_loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+    z = _rowmajor(logits)
+    gz = torch.empty(z.size(0), z.size(1), dtype=torch.float32, device=z.device)
+    L.check(_invoke('gnnb200_ce_bwd_f32', _ptr(z), _ld(z), _ptr(target.contiguous()), _ptr(lse), _ptr(g_loss.contiguous().view(1)),
+                    z.size(0), z.size(1), _ptr(gz), _ld(gz), _stream(z)), 'cross_entropy_sum backward')
+    return gz, None
+
+
+cross_entropy_sum.register_autograd(_ce_backward, setup_context=_ce_setup)
 
 
 # ---------------------------------------------------------------------------------------------

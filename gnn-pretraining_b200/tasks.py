@@ -129,7 +129,7 @@ class NodeFeatureMaskingTask(BasePretrainTask):
                 continue
             h = self.model.forward_with_h0(masked_h0, batch.edge_index)
             recon = self.model.get_head('node_feat_mask', name)(ops.rows_gather(h, idx))
-            loss = F.mse_loss(recon, target, reduction='sum')
+            loss = ops.mse_sum(recon, target)
             size = idx.size(0) * masked_h0.size(1)
             total = total + loss
             count += size
@@ -167,8 +167,7 @@ class LinkPredictionTask(BasePretrainTask):
             neg = self._negatives(batch, pos)
             edges = torch.cat([pos, neg], dim=1)
             labels = torch.cat([torch.ones(pos.size(1), device=dev), torch.zeros(neg.size(1), device=dev)])
-            probs = decoder(self.model(batch, name), edges)
-            loss = F.binary_cross_entropy(probs, labels, reduction='sum')
+            _, loss = decoder.loss(self.model(batch, name), edges, labels)      # sigmoid + BCE(sum) fused
             size = labels.size(0)
             total = total + loss
             count += size
@@ -260,7 +259,7 @@ class GraphPropertyPredictionTask(BasePretrainTask):
             emb = global_mean_pool(self.model(batch, name), batch.batch, _num_graphs(batch))
             pred = self.model.get_head('graph_prop', name)(emb)
             labels = batch.graph_properties.to(torch.float32).to(dev).view(emb.size(0), GRAPH_PROPERTY_DIM)
-            loss = F.mse_loss(pred, labels, reduction='sum')
+            loss = ops.mse_sum(pred, labels)
             size = emb.size(0) * GRAPH_PROPERTY_DIM
             total = total + loss
             count += size
@@ -284,7 +283,7 @@ class DomainAdversarialTask(BasePretrainTask):
             emb = global_mean_pool(self.model(batch, name), batch.batch, _num_graphs(batch))
             logits = self.model.get_head('domain_adv')(emb, lam)
             labels = torch.full((emb.size(0),), self.domain_to_idx[name], device=dev, dtype=torch.long)
-            loss = F.cross_entropy(logits, labels, reduction='sum')
+            loss, _ = ops.cross_entropy_sum(logits, labels)
             size = labels.size(0)
             total = total + loss
             count += size

@@ -253,6 +253,37 @@ int gnnb200_ntxent_sim_bwd_f32(float* sim, int64_t lds, int64_t two_m, float tem
                                const float* grad_loss, gnnb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Head tails and loss sums (K10: src/models/heads.py:16-24,35-50; src/pretrain/tasks.py:84,120,305,336;
+ * src/finetune/finetune.py's cross_entropy).  One launch each (a second, fixed-order finish launch beyond 2^19
+ * elements), deterministic.  All tensors dense (contiguous) unless a leading dimension is given.
+ *   act_dropout_fwd : y = dropout(relu(x)) (relu != 0; Philox stream of gnnb200_bn_act_fwd_f32 keyed by (seed, i / 4))
+ *   act_dropout_bwd : grad_x = grad_y / (1 - p) where y > 0, else 0 (the kept-and-positive mask is read off y)
+ *   scale           : y = alpha * x (gradient reversal backward: alpha = -lambda)
+ *   sqdiff_sum/_bwd : out[0] = sum (a - b)^2 = F.mse_loss(a, b, reduction='sum'); grad_a = 2 grad_loss[0] (a - b)
+ *   sigmoid_bce     : probs = sigmoid(logits); loss[0] = F.binary_cross_entropy(probs, labels, reduction='sum') incl. its
+ *                     clamp of the logarithms at -100; bwd = torch's BCE backward times sigmoid'
+ *   ce_sum          : loss[0] = F.cross_entropy(logits, target, reduction='sum'), lse [rows] saved for the backward;
+ *                     bwd: grad_logits = grad_loss[0] (softmax - onehot)
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_act_dropout_fwd_f32(const float* x, int64_t n, int relu, float drop_p, uint64_t seed, float* y,
+                                gnnb200_stream_t stream);
+int gnnb200_act_dropout_bwd_f32(const float* grad_y, const float* y, int64_t n, float drop_p, float* grad_x,
+                                gnnb200_stream_t stream);
+int gnnb200_scale_f32(const float* x, int64_t n, float alpha, float* y, gnnb200_stream_t stream);
+int gnnb200_sqdiff_sum_f32(const float* a, const float* b, int64_t n, float* out, void* workspace,
+                           size_t* workspace_bytes, gnnb200_stream_t stream);
+int gnnb200_sqdiff_bwd_f32(const float* a, const float* b, const float* grad_loss, int64_t n, float* grad_a,
+                           gnnb200_stream_t stream);
+int gnnb200_sigmoid_bce_fwd_f32(const float* logits, const float* labels, int64_t n, float* probs, float* loss,
+                                void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+int gnnb200_sigmoid_bce_bwd_f32(const float* probs, const float* labels, const float* grad_loss, int64_t n,
+                                float* grad_logits, gnnb200_stream_t stream);
+int gnnb200_ce_sum_fwd_f32(const float* logits, int64_t ldz, const int64_t* target, int64_t rows, int64_t cols, float* lse,
+                           float* loss, void* workspace, size_t* workspace_bytes, gnnb200_stream_t stream);
+int gnnb200_ce_bwd_f32(const float* logits, int64_t ldz, const int64_t* target, const float* lse, const float* grad_loss,
+                       int64_t rows, int64_t cols, float* grad_logits, int64_t ldg, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Gradient surgery on a flat buffer (src/pretrain/gradient_surgery.py:41-101).
  * task_grads [T, P] holds each task's gradient of every parameter (zeros where absent); the P
  * parameters are cut into S tensors by seg_offsets [S+1]; present [T, S] says which task produced a

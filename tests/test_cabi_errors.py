@@ -115,6 +115,19 @@ BAD = [
     ('gnnb200_ntxent_sim_fwd_f32', (D, 1 << 24, 1 << 24, 0.5, D, D, D, None), L.ERANGE),
     ('gnnb200_ntxent_sim_bwd_f32', (D, 8, 8, -1.0, D, D, None), L.EINVAL),
     ('gnnb200_ntxent_sim_bwd_f32', (None, 8, 8, 0.5, D, D, None), L.EINVAL),
+    # ---- head tails / loss sums ----
+    ('gnnb200_act_dropout_fwd_f32', (D, 16, 1, 1.0, 0, D, None), L.EINVAL),                                  # p must be < 1
+    ('gnnb200_act_dropout_fwd_f32', (None, 16, 1, 0.5, 0, D, None), L.EINVAL),
+    ('gnnb200_act_dropout_bwd_f32', (D, None, 16, 0.5, D, None), L.EINVAL),
+    ('gnnb200_scale_f32', (D, -1, 2.0, D, None), L.EINVAL),
+    ('gnnb200_sqdiff_sum_f32', (D, D, -1, D, None, 'SZ', None), L.EINVAL),
+    ('gnnb200_sqdiff_sum_f32', (D, D, 16, D, None, None, None), L.EINVAL),
+    ('gnnb200_sqdiff_bwd_f32', (D, D, None, 16, D, None), L.EINVAL),
+    ('gnnb200_sigmoid_bce_fwd_f32', (D, D, -1, D, D, None, 'SZ', None), L.EINVAL),
+    ('gnnb200_sigmoid_bce_bwd_f32', (D, D, D, 16, None, None), L.EINVAL),
+    ('gnnb200_ce_sum_fwd_f32', (D, 4, D, 16, 0, D, D, None, 'SZ', None), L.EINVAL),                          # no classes
+    ('gnnb200_ce_sum_fwd_f32', (D, 4, D, 16, 1 << 20, D, D, None, 'SZ', None), L.ERANGE),
+    ('gnnb200_ce_bwd_f32', (D, 2, D, D, D, 16, 4, D, 4, None), L.EINVAL),                                    # ldz < cols
     # ---- gradient surgery ----
     ('gnnb200_pcgrad_f32', (D, D, -1, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, None, 2, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
