@@ -76,6 +76,8 @@ SIGNATURES = {
     'gnnb200_sigmoid_bce_bwd_f32': [P, P, P, I64, P, P],
     'gnnb200_ce_sum_fwd_f32': [P, I64, P, I64, I64, P, P, P, SZP, P],
     'gnnb200_ce_bwd_f32': [P, I64, P, P, P, I64, I64, P, I64, P],
+    'gnnb200_negsample_count_i64': [P, I64, P, P, I64, P, I64, P, P, P],
+    'gnnb200_negsample_write_i64': [P, I64, P, P, I64, P, P, I64, P, P],
     'gnnb200_pcgrad_f32': [P, P, I64, I64, P, I64, P, P, P, P, P, P, P],
     'gnnb200_aggregate_peer_f32': [P, c_int, I64, P, P, I64, I64, P, I64, P, P, I64, P],
     'gnnb200_peer_publish_f32': [P, I64, I64, I64, P, I64, P],

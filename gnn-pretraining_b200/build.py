@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgnnb200.so')
 SOURCES = ['api.cu', 'csr.cu', 'aggregate.cu', 'pool.cu', 'reduce.cu', 'rows.cu', 'gemm_simt.cu',
-           'gemm_tcgen05.cu', 'ntxent.cu', 'bn.cu', 'pcgrad.cu', 'elementwise_v2.cu', 'aggregate_peer.cu', 'gin_layer.cu', 'heads.cu']
+           'gemm_tcgen05.cu', 'ntxent.cu', 'bn.cu', 'pcgrad.cu', 'elementwise_v2.cu', 'aggregate_peer.cu', 'gin_layer.cu', 'heads.cu', 'negsample.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

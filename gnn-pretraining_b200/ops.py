@@ -105,7 +105,7 @@ KERNELS_PER_CALL = {
     'gnnb200_bn_finalize_f32': 1, 'gnnb200_bn_merge_finalize_f32': 1, 'gnnb200_bn_act_fwd_f32': 1, 'gnnb200_bn_act_bwd_f32': 3,
     'gnnb200_act_dropout_fwd_f32': 1, 'gnnb200_act_dropout_bwd_f32': 1, 'gnnb200_scale_f32': 1, 'gnnb200_sqdiff_sum_f32': 1,
     'gnnb200_sqdiff_bwd_f32': 1, 'gnnb200_sigmoid_bce_fwd_f32': 1, 'gnnb200_sigmoid_bce_bwd_f32': 1, 'gnnb200_ce_sum_fwd_f32': 1,
-    'gnnb200_ce_bwd_f32': 1,
+    'gnnb200_ce_bwd_f32': 1, 'gnnb200_negsample_count_i64': 1, 'gnnb200_negsample_write_i64': 1,
     'gnnb200_lp_features_f32': 1, 'gnnb200_lp_features_bwd_f32': 1, 'gnnb200_ntxent_fwd_f32': 3,
     'gnnb200_ntxent_bwd_f32': 1, 'gnnb200_pcgrad_f32': 2, 'gnnb200_normalize_rows_f32': 1,
     'gnnb200_normalize_rows_bwd_f32': 1, 'gnnb200_ntxent_sim_fwd_f32': 2, 'gnnb200_ntxent_sim_bwd_f32': 1,

@@ -107,12 +107,50 @@ def batched_negative_sampling(edge_index: Tensor, batch: Tensor, num_neg_samples
     e_total = edge_index.size(1)
     if e_total == 0:
         return edge_index.new_empty((2, 0))
+    if ops.on_device(edge_index) and edge_index.is_cuda:
+        found = _batched_negative_sampling_device(edge_index, batch, e_total if num_neg_samples is None else int(num_neg_samples))
+        if found is not None:
+            return found
     host = torch.cat([edge_index.reshape(-1), batch]).cpu().numpy()
     ei, graph_of_node = host[:2 * e_total].reshape(2, e_total), host[2 * e_total:]
     found = batched_negative_sampling_host(ei, np.bincount(graph_of_node), num_neg_samples)
     if found is None:
         return edge_index.new_empty((2, 0))
     return torch.from_numpy(found).to(edge_index.device)
+
+
+def _batched_negative_sampling_device(edge_index: Tensor, batch: Tensor, quota: int) -> Optional[Tensor]:
+    """The deterministic branch as a bitmap complement on the device (csrc/negsample.cu): two launches, a scan and ONE
+    read-back (the output width and whether some graph needs Python's `random`, in which case None sends the caller to
+    the host sampler so that stream is consumed exactly as upstream)."""
+    from . import _lib as L
+    from .graph import segment_ptr_of
+    ei = edge_index.contiguous()
+    e_total = ei.size(1)
+    node_ptr = segment_ptr_of(batch)                       # int32 [G + 1], cached on the batch vector
+    num_graphs = node_ptr.numel() - 1
+    graph_of_edge = batch[ei[0]]
+    edge_ptr = ops.segment_ptr(graph_of_edge, num_graphs)
+    counts = torch.empty(num_graphs, dtype=torch.int64, device=ei.device)
+    state = torch.zeros(3, dtype=torch.int64, device=ei.device)          # [total, needs_host (written as int32), ungrouped]
+    stream = ops._stream(ei)
+    L.check(ops._invoke('gnnb200_negsample_count_i64', ei.data_ptr(), e_total, node_ptr.data_ptr(), edge_ptr.data_ptr(),
+                        num_graphs, graph_of_edge[-1:].data_ptr(), quota, counts.data_ptr(), state[1:].data_ptr(), stream),
+            'negsample_count')
+    ends = torch.cumsum(counts, 0)
+    state[0:1] = ends[-1:]
+    state[2:3] = (graph_of_edge[1:] < graph_of_edge[:-1]).any()
+    total, needs_host, ungrouped = state.tolist()                         # the one device -> host read
+    if ungrouped:
+        raise ValueError('edge_index columns must be grouped by graph (to_undirected / Batch order)')
+    if needs_host:
+        return None
+    out = torch.empty(2, total, dtype=torch.int64, device=ei.device)
+    if total:
+        L.check(ops._invoke('gnnb200_negsample_write_i64', ei.data_ptr(), e_total, node_ptr.data_ptr(), edge_ptr.data_ptr(),
+                            num_graphs, counts.data_ptr(), (ends - counts).data_ptr(), total, out.data_ptr(), stream),
+                'negsample_write')
+    return out
 
 
 def to_undirected_host(edge_index: np.ndarray, num_nodes: int) -> np.ndarray:

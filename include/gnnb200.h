@@ -253,6 +253,25 @@ int gnnb200_ntxent_sim_bwd_f32(float* sim, int64_t lds, int64_t two_m, float tem
                                const float* grad_loss, gnnb200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched negative sampling, deterministic branch (src/pretrain/tasks.py:107-111 -> PyG
+ * batched_negative_sampling, App. A.5): for every graph whose sampler would draw arange(population) — all TU-sized graphs at
+ * the reference's call site — the negatives are ALL its non-edges in ascending code order, truncated to `quota`.
+ *   edge_index int64 [2, E] with columns grouped by graph (to_undirected order); node_ptr int32 [G+1] (Batch.ptr);
+ *   edge_ptr int32 [G+1] = column ranges per graph; last_graph -> int64 on the device = graph of the last column (graphs
+ *   behind it are skipped, like upstream); quota = num_neg_samples (the batch's edge count at the call site).
+ *   count: counts [G] int64 = negatives per graph; *needs_host (int32, caller zeroes it) is raised when some graph takes
+ *          upstream's random.sample branch or has more than 724 nodes — the caller then uses the host sampler instead.
+ *   write: out int64 [2, total] (total = sum(counts), offsets = exclusive scan of counts), node ids with the batch offsets.
+ * Integer work: bit-exact with the oracle.
+ * ------------------------------------------------------------------------------------------ */
+int gnnb200_negsample_count_i64(const int64_t* edge_index, int64_t num_edges, const int32_t* node_ptr,
+                                const int32_t* edge_ptr, int64_t num_graphs, const int64_t* last_graph, int64_t quota,
+                                int64_t* counts, int32_t* needs_host, gnnb200_stream_t stream);
+int gnnb200_negsample_write_i64(const int64_t* edge_index, int64_t num_edges, const int32_t* node_ptr,
+                                const int32_t* edge_ptr, int64_t num_graphs, const int64_t* counts, const int64_t* offsets,
+                                int64_t total, int64_t* out, gnnb200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Head tails and loss sums (K10: src/models/heads.py:16-24,35-50; src/pretrain/tasks.py:84,120,305,336;
  * src/finetune/finetune.py's cross_entropy).  One launch each (a second, fixed-order finish launch beyond 2^19
  * elements), deterministic.  All tensors dense (contiguous) unless a leading dimension is given.

@@ -128,6 +128,12 @@ BAD = [
     ('gnnb200_ce_sum_fwd_f32', (D, 4, D, 16, 0, D, D, None, 'SZ', None), L.EINVAL),                          # no classes
     ('gnnb200_ce_sum_fwd_f32', (D, 4, D, 16, 1 << 20, D, D, None, 'SZ', None), L.ERANGE),
     ('gnnb200_ce_bwd_f32', (D, 2, D, D, D, 16, 4, D, 4, None), L.EINVAL),                                    # ldz < cols
+    # ---- negative sampling ----
+    ('gnnb200_negsample_count_i64', (D, 10, D, D, 4, D, -1, D, D, None), L.EINVAL),                            # negative quota
+    ('gnnb200_negsample_count_i64', (D, 10, D, D, 4, None, 10, D, D, None), L.EINVAL),
+    ('gnnb200_negsample_count_i64', (D, BIG, D, D, 4, D, 10, D, D, None), L.ERANGE),
+    ('gnnb200_negsample_write_i64', (D, 10, D, D, 4, D, D, -1, D, None), L.EINVAL),
+    ('gnnb200_negsample_write_i64', (D, 10, D, D, 4, D, None, 10, D, None), L.EINVAL),
     # ---- gradient surgery ----
     ('gnnb200_pcgrad_f32', (D, D, -1, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, None, 2, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
