@@ -138,9 +138,11 @@ def build_model(impl_models, device, f_in, seed=0):
 
 
 def step_fn(model, opt, x, edge_index):
-    """One training step of the hot path.  `edge_index.view_as` gives a fresh tensor object, so the
-    CSR/CSC build is part of every step (no cached structure carried across steps)."""
-    ei = edge_index.view_as(edge_index)
+    """One training step of the hot path.  The sorted CSR / CSC of `edge_index` is cached on the tensor object until it is
+    overwritten (gnnb200.graph.graph_of; SURVEY §8d: a one-off cost amortised over every pass on that graph): the
+    device-resident leg builds it once (reported as `structure_build_ms`), the end-to-end leg — whose edge list arrives
+    from the host every step — rebuilds it every step."""
+    ei = edge_index
     opt.zero_grad(set_to_none=True)
     h = model['gnn_backbone'](model['input_encoder'](x), ei)
     loss = h.sum()
@@ -213,7 +215,10 @@ def partition_selfcheck(prod, dev, rank, world, halo):
                             'fwd_max_rel': float((h_all - ref[1]).abs().max() / ref[1].abs().max()),
                             'loss_partitioned': float(total), 'loss_rel': abs(float(total) - ref[2]) / abs(ref[2]),
                             'grad_fro': float((g - ref[3]).norm() / ref[3].norm())})
-                out['ok'] = bool(out['aggregation_bitwise'] and out['fwd_max_rel'] < 1e-3 and out['grad_fro'] < 2e-2)
+                out['aggregation_max_rel'] = float((z_all - ref[0]).abs().max() / ref[0].abs().max())
+                # 'sparse_overlap' sums a row's local neighbours before its remote ones: fp32 rounding, not bit identity
+                exact = out['aggregation_bitwise'] or (graph.halo == 'sparse_overlap' and out['aggregation_max_rel'] < 1e-5)
+                out['ok'] = bool(exact and out['fwd_max_rel'] < 1e-3 and out['grad_fro'] < 2e-2)
     finally:
         prod.DROPOUT_RATE = old_p
     del data, x, ei, w
@@ -259,6 +264,22 @@ def run_product(args):
     selfcheck = None if args.no_selfcheck else partition_selfcheck(prod, dev, rank, world, args.halo)
 
     # ---- device-resident leg -----------------------------------------------------------------
+    # the graph structure (CSR + CSC on one GPU; ownership scan, sorts and halo plan when partitioned), timed on its own
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    b0.record()
+    if world > 1:
+        runner.graph_of(ei_dev)
+    else:
+        from gnnb200.graph import graph_of as _graph_of
+        _g = _graph_of(ei_dev, n)
+        _g.rowptr_t                                  # the by-source CSR of the backward pass
+    b1.record()
+    barrier()
+    tb = torch.tensor([b0.elapsed_time(b1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    structure_ms = float(tb)
     loss0 = None
     for i in range(args.warmup):
         l_ = one_step(x_dev, ei_dev)
@@ -391,11 +412,13 @@ def run_product(args):
             'scaling': 'strong', 'vs_baseline': None, 'dtype': DTYPE_NAMES[gnn.default_precision()],
             'data': 'synthetic',
             'config': {'workload': 'c5_products_backbone', 'nodes': n, 'edges': e, 'feat_in': C5_F,
-                       'hidden': HIDDEN, 'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
+                       'hidden': HIDDEN, 'layers': LAYERS,
+                       'mode': 'train fwd+bwd+AdamW; graph structure built once per edge list (every step in the e2e leg)',
                        'edge_locality': args.locality, 'degree_skew': args.skew, 'gemm_precision': gnn.default_precision(),
                        'l2_policy': 'inputs_larger_than_L2 (2.5 GB activations per layer vs 126 MB L2)',
                        'parallelism': 'single' if world == 1 else f'node_partition{world}+' + (
-                           {'sparse': 'halo_alltoall_sparse', 'peer': 'halo_read_in_gather_over_nvlink_peer_memory',
+                           {'sparse': 'halo_alltoall_sparse', 'sparse_overlap': 'halo_alltoall_sparse_overlapped_with_local_gather',
+                            'peer': 'halo_read_in_gather_over_nvlink_peer_memory',
                             'peercopy': 'halo_allgather_by_copy_engines'}.get(
                                runner.last_halo, 'halo_allgather'))},
             'clocks': clocks.summary(),
@@ -403,7 +426,7 @@ def run_product(args):
                     'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4,
                     'note': 'inputs from pinned host memory every step (H2D on a side stream, prefetched one step ahead), loss read back every step'},
             'gpu_launches': launches,
-            'selfcheck': selfcheck, 'loss_step0': loss0,
+            'selfcheck': selfcheck, 'loss_step0': loss0, 'structure_build_ms': structure_ms,
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30,
             'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM,2,6> (fwd and transposed bwd)',
                          'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
@@ -769,7 +792,7 @@ def run_reference(args):
         'dtype': 'f32', 'data': 'synthetic',
         # the arm's own config (the rate is per edge, so a sample of the workload measures the same metric)
         'config': {'workload': 'c5_products_backbone', 'nodes': n_full, 'edges': e_full, 'feat_in': C5_F, 'hidden': HIDDEN,
-                   'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW, CSR/CSC build every step',
+                   'layers': LAYERS, 'mode': 'train fwd+bwd+AdamW; graph structure built once per edge list (every step in the e2e leg)',
                    'edge_locality': args.locality, 'degree_skew': args.skew,
                    'sampled_step': {'nodes': n, 'edges': e, 'fraction': frac,
                                     'why': 'CPU step on the full graph takes minutes and ~190 GB of transient messages'}},
@@ -862,7 +885,7 @@ def main():
     ap.add_argument('--skew', type=float, default=0.0,
                     help='> 1: power-law endpoints (1.8 ~ ogbn-products: largest hub 2.8e-4 of all edges); 0 = uniform (default)')
     ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3', 'tf32_fwd3'])
-    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'auto', 'peer', 'peercopy'],
+    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'sparse_overlap', 'auto', 'peer', 'peercopy'],
                     help='N > 1: rows exchanged per layer (default dense = all-gather; see gnnb200/partition.py)')
     ap.add_argument('--cpu-sample', type=float, default=None, dest='cpu_sample',
                     help='fraction of the workload per CPU step (default: 1/16 for cpu_baseline; --impl reference picks up to 1/4 by time and memory)')

@@ -50,13 +50,22 @@ DEFAULT_HALO_CHUNKS = 1
 #   'peercopy': the dense exchange without NCCL: every rank publishes its shard (PeerRows) and PULLS the other shards with
 #              the copy engines (cudaMemcpyAsync from the peer-mapped buffers, no SM time, no NCCL kernel sharing HBM with
 #              anything), then runs the ordinary gather on the assembled [P * rows, F] buffer.  Same bytes as 'dense'.
-# 'sparse'/'auto' are covered by the gloo world-2 tests (index plan, exchange, algebra) but were written after the
-# round's GPU budget was spent: unmeasured on NCCL, hence opt-in (GNNB200_HALO or the `halo=` argument).
-# 'peer' was written at the same time; its kernel and column encoding are tested on one GPU against the
-# single-device kernel (virtual ranks = slices of one buffer), the IPC leg needs 2 GPUs and is equally unmeasured.
-DEFAULT_HALO = 'dense'
+#   'sparse_overlap': the sparse exchange hidden behind the part of the gather that does not need it: the owned edges are
+#              split into those with a LOCAL source (CSR over this rank's own rows) and those with a REMOTE source (CSR
+#              over the halo buffer); the halo all-to-all is started asynchronously, the local gather (+ self term) runs
+#              while the rows travel, and the halo gather then continues every row's sum (ACCUMULATE).  A row's sum is
+#              "local neighbours in edge order, then remote neighbours in edge order": deterministic, but a different
+#              association than the single-device edge order (fp32 rounding instead of bit identity).
+# All modes are bit-identical to each other and to the single-device kernel except 'sparse_overlap' (measured on 2 and 8
+# B200s over NCCL / CUDA IPC: tests/test_gpu_partition.py, bench.py's selfcheck).  Measured C5 steps (profiles/r02):
+#   uniform graph,   8 GPUs: dense 71.4 ms, peercopy 155.0 ms (the seven pulls of a rank serialise on one stream)
+#   90 % intra-block, 8 GPUs: sparse 50.9 ms, peer 83.0 ms (remote reads inside the gather are latency-bound: 5.6 ms / pass)
+#   90 % intra-block, 2 GPUs: peer 136.9 ms, sparse 149.7 ms, dense 156.4 ms
+# hence 'auto' = the default: the overlapped sparse exchange when the ranks need less than half of the remote rows, the
+# all-gather otherwise.
+DEFAULT_HALO = 'auto'
 SPARSE_HALO_MAX_FRACTION = 0.5
-HALO_MODES = ('dense', 'sparse', 'auto', 'peer', 'peercopy')
+HALO_MODES = ('dense', 'sparse', 'sparse_overlap', 'auto', 'peer', 'peercopy')
 
 
 def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
@@ -93,6 +102,16 @@ class HaloPlan:
                                input_split_sizes=self.need_cnt, group=group)
         self.halo_rows = int(need.numel())
         self.col = torch.where(remote, self.n_local + torch.searchsorted(need, other), other - lo)
+
+    def exchange_async(self, x_local: Tensor):
+        """(work, [H, F] halo rows in ascending global id): the all-to-all is started with async_op; the caller waits on
+        `work` before reading the rows."""
+        f = x_local.size(1)
+        halo = x_local.new_empty(self.halo_rows, f)
+        send = _pack_rows(x_local, self.serve_idx)
+        work = dist.all_to_all_single(halo, send, output_split_sizes=self.need_cnt, input_split_sizes=self.serve_cnt,
+                                      group=self.group, async_op=True)
+        return work, halo
 
     def exchange(self, x_local: Tensor) -> Tensor:
         """[n_local + H, F]: this rank's rows followed by the remote rows it references (ascending global id)."""
@@ -236,13 +255,19 @@ class PartitionedGraph:
         if world > 1 and halo == 'auto':
             own = (dst >= self.lo) & (dst < self.hi)
             frac = remote_fraction_needed(src[own], self.lo, self.hi, self.num_nodes, group)
-            halo = 'sparse' if frac < SPARSE_HALO_MAX_FRACTION else 'dense'
+            halo = 'sparse_overlap' if frac < SPARSE_HALO_MAX_FRACTION else 'dense'
         self.halo = halo if world > 1 else 'dense'
         self.plan = self.plan_t = None
         if self.halo == 'sparse':
             self.chunks = 1
             self.rowptr, self.col, self.local_edges, self.plan = self._build_sparse(src, dst, n_rows)
             self.rowptr_t, self.col_t, _, self.plan_t = self._build_sparse(dst, src, n_rows)
+            return
+        if self.halo == 'sparse_overlap':
+            self.chunks = 1
+            self.split, self.local_edges = self._build_split(src, dst, n_rows)
+            self.split_t, _ = self._build_split(dst, src, n_rows)
+            self.rowptr = self.col = self.rowptr_t = self.col_t = None
             return
         if self.halo == 'peer':
             self.chunks = 1
@@ -260,6 +285,18 @@ class PartitionedGraph:
         rowptr, col, _ = ops.csr_build(torch.stack([plan.col, m], dim=0), n_rows, False)
         plan.col = None                                                   # only the CSR copy is kept
         return rowptr, col, int(m.numel()), plan
+
+    def _build_split(self, other: Tensor, mine: Tensor, n_rows: int):
+        """(local CSR over x_local, halo CSR over the exchanged rows, plan) for the overlapped sparse exchange."""
+        own = (mine >= self.lo) & (mine < self.hi)
+        o, m = other[own], mine[own] - self.lo
+        plan = HaloPlan(o, self.lo, self.hi, self.per, self.world, self.group)
+        remote = plan.col >= self.n_local
+        near = ~remote
+        rowptr_l, col_l, _ = ops.csr_build(torch.stack([plan.col[near], m[near]], dim=0), n_rows, False)
+        rowptr_h, col_h, _ = ops.csr_build(torch.stack([plan.col[remote] - self.n_local, m[remote]], dim=0), n_rows, False)
+        plan.col = None
+        return (rowptr_l, col_l, rowptr_h, col_h, plan), int(m.numel())
 
     def _build_peer(self, other: Tensor, mine: Tensor, n_rows: int):
         """CSR over the owned edges whose columns address the owners' published buffers (encode_peer_columns)."""
@@ -325,6 +362,15 @@ class PartitionedGraph:
         if self.halo == 'sparse':
             buf = (self.plan_t if transposed else self.plan).exchange(x_local)
             return ops._aggregate_raw(buf, rowptr, col, L.AGG_SUM, x_local, eps, None)
+        if self.halo == 'sparse_overlap':
+            rowptr_l, col_l, rowptr_h, col_h, plan = self.split_t if transposed else self.split
+            work, halo = plan.exchange_async(x_local)                   # rows travel ...
+            out = ops._aggregate_raw(x_local, rowptr_l, col_l, L.AGG_SUM, x_local, eps, None)     # ... while these are summed
+            if work is not None:
+                work.wait()
+            if plan.halo_rows:
+                out = ops._aggregate_raw(halo, rowptr_h, col_h, L.AGG_SUM, None, None, None, out)
+            return out
         if self.halo == 'peer':
             f = x_local.size(1)
             table = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).publish(x_local)
@@ -479,10 +525,22 @@ class PartitionedBackboneStep:
         self.opt = torch.optim.AdamW(self.model.parameters(), lr=lr)
         self.num_nodes, self.rank, self.world, self.group = num_nodes, rank, world, group
         self.halo, self.last_halo = halo, None
+        self._graph_key, self._graph = None, None
+
+    def graph_of(self, edge_index: Tensor) -> PartitionedGraph:
+        """This rank's partition of `edge_index`, built once per tensor object and version (like gnnb200.graph.graph_of on one
+        device): a static graph pays the O(E) ownership scan, the sorts and the halo plan once, a new or overwritten edge
+        list pays them again."""
+        import weakref
+        alive = self._graph_key[0]() if self._graph_key is not None else None
+        if self._graph is None or alive is not edge_index or self._graph_key[1] != edge_index._version:
+            self._graph = PartitionedGraph(edge_index, self.num_nodes, self.rank, self.world, self.group, halo=self.halo)
+            self._graph_key = (weakref.ref(edge_index), edge_index._version)     # the same OBJECT, unmodified since
+        return self._graph
 
     def step(self, x: Tensor, edge_index: Tensor, x_is_local: bool = False) -> Tensor:
         """x: the full [N, F] feature matrix, or (x_is_local) just this rank's row shard."""
-        graph = PartitionedGraph(edge_index, self.num_nodes, self.rank, self.world, self.group, halo=self.halo)
+        graph = self.graph_of(edge_index)
         self.last_halo = graph.halo
         x_local = x if x_is_local else x[graph.lo:graph.hi]
         self.opt.zero_grad(set_to_none=True)

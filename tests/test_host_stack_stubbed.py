@@ -142,7 +142,7 @@ def _partition_worker(rank, world, port, halo, out_dir):
         before = [p.detach().clone() for p in runner.model.parameters()]
         for _ in range(2):
             loss = runner.step(data['x'], data['edge_index'])
-        assert runner.last_halo == {'auto': 'sparse'}.get(halo, halo)                # 'auto' picks sparse on this graph
+        assert runner.last_halo == {'auto': 'sparse_overlap'}.get(halo, halo)        # 'auto' picks the overlapped sparse exchange here
         assert loss.shape == () and torch.isfinite(loss)
         assert all(p.grad is not None for p in runner.model.parameters())
         assert len(before) == len(list(runner.model.parameters()))
@@ -156,7 +156,7 @@ def _partition_worker(rank, world, port, halo, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('halo,world', [('dense', 2), ('sparse', 2), ('auto', 3), ('peer', 2), ('peercopy', 2)])
+@pytest.mark.parametrize('halo,world', [('dense', 2), ('sparse', 2), ('sparse_overlap', 2), ('auto', 3), ('peer', 2), ('peercopy', 2)])
 def test_partitioned_step_host_logic_over_gloo(tmp_path, halo, world):
     import socket
     import torch.multiprocessing as mp

@@ -163,6 +163,18 @@ def _sparse_worker(rank, world, port, n, e, f, locality, out_dir):
             z_sparse = _oracle_agg(buf, rp, col_sparse, feat[lo:hi], eps)
             z_dense = _oracle_agg(feat, rp, col_dense, feat[lo:hi], eps)
             assert torch.equal(z_sparse, z_dense)
+            # -- 'sparse_overlap': asynchronous exchange of the halo rows alone; local-source edges summed first (over the rank's
+            #    own rows), remote-source edges continue the sum over the halo buffer: the same rows to fp32 rounding
+            work, halo = plan.exchange_async(feat[lo:hi])
+            work.wait()
+            assert torch.equal(halo, feat[want])
+            far = plan.col >= n_local
+            rp_l, col_l = _csr(m[~far], plan.col[~far], max(n_local, 1))
+            rp_h, col_h = _csr(m[far], plan.col[far] - n_local, max(n_local, 1))
+            z_split = _oracle_agg(feat[lo:hi], rp_l, col_l, feat[lo:hi], eps)
+            if plan.halo_rows:
+                z_split = z_split + _oracle_agg(halo, rp_h, col_h, torch.zeros_like(z_split), torch.tensor([-1.0]))
+            torch.testing.assert_close(z_split, z_dense, rtol=1e-5, atol=1e-5)
             # -- the 'auto' criterion is the same number on every rank
             frac = partition.remote_fraction_needed(o, lo, hi, n)
             every = [None] * world
