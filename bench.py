@@ -392,6 +392,33 @@ def run_product(args):
     e2e_ms = float(t2) / args.steps
     e2e_value = e * LAYERS * 2 / (e2e_ms / 1e3)
 
+    # ---- generator (ii) of SURVEY §8d.5 beside the headline (which runs generator (i), uniform-random edges = worst-case
+    #      locality): power-law degrees + 90 % intra-block edges, the same step on the same model, device-resident ----
+    gen2 = None
+    if not args.no_generator2 and args.locality == 0.0 and args.skew == 0.0:
+        pending[0] = None
+        slots.clear()
+        torch.cuda.empty_cache()
+        d2 = make_graph(n, e, C5_F, 42, 0.9, dev, 1.8)
+        x2, ei2 = d2['x'], d2['edge_index']
+        for _ in range(2):
+            one_step(x2, ei2)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            one_step(x2, ei2)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        g_ms = float(tg) / args.steps
+        gen2 = {'generator': '(ii) power-law degrees (skew 1.8) + 90 % intra-block edges (block = N/64)', 'ms_per_step': g_ms,
+                'value': e * LAYERS * 2 / (g_ms / 1e3), 'unit': UNIT,
+                'halo': runner.last_halo if world > 1 else None}
+        del d2, x2, ei2
+
     out = None
     if rank == 0:
         pk = peaks()
@@ -426,7 +453,7 @@ def run_product(args):
                     'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4,
                     'note': 'inputs from pinned host memory every step (H2D on a side stream, prefetched one step ahead), loss read back every step'},
             'gpu_launches': launches,
-            'selfcheck': selfcheck, 'loss_step0': loss0, 'structure_build_ms': structure_ms,
+            'selfcheck': selfcheck, 'loss_step0': loss0, 'structure_build_ms': structure_ms, 'generator_ii': gen2,
             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30,
             'roofline': {'bound': 'hbm', 'kernel': 'aggregate_vec_kernel<32,2,SUM,2,6> (fwd and transposed bwd)',
                          'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
@@ -891,6 +918,7 @@ def main():
                     help='fraction of the workload per CPU step (default: 1/16 for cpu_baseline; --impl reference picks up to 1/4 by time and memory)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs only: skip the end-to-end leg')
+    ap.add_argument('--no-generator2', action='store_true', dest='no_generator2', help='skip the secondary run on generator (ii)')
     ap.add_argument('--no-selfcheck', action='store_true', help='profiling runs only: skip the parity check before the timed region')
     ap.add_argument('--no-secondary', action='store_true', help='skip the small-graph configs (C1 backbone, C2 fine-tune step, C3 s4 step)')
     ap.add_argument('--secondary-steps', type=int, default=40, dest='secondary_steps', help='timed steps per small-graph config with --only-secondary')

@@ -258,10 +258,12 @@ class PartitionedGraph:
             halo = 'sparse_overlap' if frac < SPARSE_HALO_MAX_FRACTION else 'dense'
         self.halo = halo if world > 1 else 'dense'
         self.plan = self.plan_t = None
+        self.long_rows = self.long_rows_t = None
         if self.halo == 'sparse':
             self.chunks = 1
             self.rowptr, self.col, self.local_edges, self.plan = self._build_sparse(src, dst, n_rows)
             self.rowptr_t, self.col_t, _, self.plan_t = self._build_sparse(dst, src, n_rows)
+            self._find_long_rows()
             return
         if self.halo == 'sparse_overlap':
             self.chunks = 1
@@ -276,6 +278,14 @@ class PartitionedGraph:
             return
         self.rowptr, self.col, self.local_edges = self._build(src, dst, n_rows)       # own destinations
         self.rowptr_t, self.col_t, _ = self._build(dst, src, n_rows)                  # own sources (transposed)
+        if self.chunks == 1:
+            self._find_long_rows()
+
+    def _find_long_rows(self) -> None:
+        """Hub rows of this rank's CSRs (gnnb200.graph.long_rows_of): they take the block-per-row kernel, as on one device."""
+        from .graph import long_rows_of
+        self.long_rows = long_rows_of(self.rowptr, int(self.col.numel()))
+        self.long_rows_t = long_rows_of(self.rowptr_t, int(self.col_t.numel()))
 
     def _build_sparse(self, other: Tensor, mine: Tensor, n_rows: int):
         """CSR over the owned edges whose columns index the sparse exchange buffer (HaloPlan)."""
@@ -293,9 +303,12 @@ class PartitionedGraph:
         plan = HaloPlan(o, self.lo, self.hi, self.per, self.world, self.group)
         remote = plan.col >= self.n_local
         near = ~remote
+        from .graph import long_rows_of
         rowptr_l, col_l, _ = ops.csr_build(torch.stack([plan.col[near], m[near]], dim=0), n_rows, False)
         rowptr_h, col_h, _ = ops.csr_build(torch.stack([plan.col[remote] - self.n_local, m[remote]], dim=0), n_rows, False)
         plan.col = None
+        plan.long_local = long_rows_of(rowptr_l, int(col_l.numel()))
+        plan.long_halo = long_rows_of(rowptr_h, int(col_h.numel()))
         return (rowptr_l, col_l, rowptr_h, col_h, plan), int(m.numel())
 
     def _build_peer(self, other: Tensor, mine: Tensor, n_rows: int):
@@ -359,17 +372,19 @@ class PartitionedGraph:
         rowptr, col = (self.rowptr_t, self.col_t) if transposed else (self.rowptr, self.col)
         if self.world == 1:
             return ops._aggregate_raw(x_local, rowptr, col, L.AGG_SUM, x_local, eps, None)
+        long_rows = self.long_rows_t if transposed else self.long_rows
         if self.halo == 'sparse':
             buf = (self.plan_t if transposed else self.plan).exchange(x_local)
-            return ops._aggregate_raw(buf, rowptr, col, L.AGG_SUM, x_local, eps, None)
+            return ops._aggregate_raw(buf, rowptr, col, L.AGG_SUM, x_local, eps, None, long_rows=long_rows)
         if self.halo == 'sparse_overlap':
             rowptr_l, col_l, rowptr_h, col_h, plan = self.split_t if transposed else self.split
             work, halo = plan.exchange_async(x_local)                   # rows travel ...
-            out = ops._aggregate_raw(x_local, rowptr_l, col_l, L.AGG_SUM, x_local, eps, None)     # ... while these are summed
+            out = ops._aggregate_raw(x_local, rowptr_l, col_l, L.AGG_SUM, x_local, eps, None,     # ... while these are summed
+                                     long_rows=plan.long_local)
             if work is not None:
                 work.wait()
             if plan.halo_rows:
-                out = ops._aggregate_raw(halo, rowptr_h, col_h, L.AGG_SUM, None, None, None, out)
+                out = ops._aggregate_raw(halo, rowptr_h, col_h, L.AGG_SUM, None, None, None, out, long_rows=plan.long_halo)
             return out
         if self.halo == 'peer':
             f = x_local.size(1)
@@ -378,14 +393,15 @@ class PartitionedGraph:
         if self.halo == 'peercopy':
             f = x_local.size(1)
             full = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).gather_all(x_local)
-            return ops._aggregate_raw(full, rowptr, col, L.AGG_SUM, x_local, eps, None)
+            return ops._aggregate_raw(full, rowptr, col, L.AGG_SUM, x_local, eps, None, long_rows=long_rows)
         pieces = self.gather_pieces_async(x_local)
         out = None
         for c, (work, buf) in enumerate(pieces):
             work.wait()                                   # current stream waits for piece c only
             last = c == self.chunks - 1
             out = ops._aggregate_raw(buf, self.sub_rowptr(rowptr, c), col, L.AGG_SUM,
-                                     x_local if last else None, eps if last else None, None, out)
+                                     x_local if last else None, eps if last else None, None, out,
+                                     long_rows=long_rows if self.chunks == 1 else None)
         return out
 
 

@@ -3,7 +3,7 @@
 # every kernel family of one training step at quarter scale (612 k rows: far beyond L2) — forward pass, then backward pass.
 set -u
 mkdir -p gpurun_out
-FULL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary --no-e2e --no-selfcheck"
+FULL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-secondary --no-e2e --no-selfcheck --no-generator2"
 QUARTER="$FULL --scale 0.25"
 $FULL > gpurun_out/r02d_plain_full.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02d_launches_full_scale.csv $FULL > gpurun_out/r02d_ncu_launches.log 2>&1
