@@ -300,14 +300,19 @@ def _(edge_index, num_nodes):
 # ---------------------------------------------------------------------------------------------
 def _aggregate_raw(x: Tensor, rowptr: Tensor, col: Tensor, mode: int, self_x: Optional[Tensor],
                    eps: Optional[Tensor], dinv: Optional[Tensor], out: Optional[Tensor] = None,
-                   long_rows: Optional[Tensor] = None) -> Tensor:
+                   long_rows: Optional[Tensor] = None, dst: Optional[Tensor] = None) -> Tensor:
     """out given => accumulate into it (GNNB200_AGG_ACCUMULATE): a later pass of a chunked aggregation.
+    dst given => write the result there (e.g. a column slab of a wider matrix: any leading dimension), no accumulation.
     long_rows (int64 ids of the rows with more than L.AGG_LONG_ROW neighbours, SUM mode): the main launch skips them and a
     block-per-row kernel covers them (gnnb200_aggregate_long_rows_f32)."""
     _need_cuda(x, rowptr, col, self_x, eps, dinv)
     x = _rowmajor(x)
     n_rows = rowptr.numel() - 1
-    if out is None:
+    if dst is not None:
+        if out is not None or dst.shape != (n_rows, x.size(1)) or dst.stride(1) != 1:
+            raise L.Gnnb200Error('aggregate: dst must be a [rows, F] view with unit inner stride (and no `out`)')
+        out = dst
+    elif out is None:
         out = torch.empty(n_rows, x.size(1), dtype=torch.float32, device=x.device)
     else:
         mode |= L.AGG_ACCUMULATE

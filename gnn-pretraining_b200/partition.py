@@ -30,6 +30,11 @@ from . import ops
 # back, because every remote row is needed and the exchange, not the gather, is the long pole.  Pipelining pays when
 # the local gather is longer than the exchange (few ranks, high-degree graphs); it stays opt-in.
 DEFAULT_HALO_CHUNKS = 1
+# The dense exchange is pipelined over COLUMN slabs instead: the [rows, F] shard is all-gathered as `slabs` matrices of F/slabs
+# columns (all started asynchronously) and slab c is gathered while slabs c+1.. are still in flight.  Unlike the row pieces
+# every pass walks whole neighbour lists and writes its own columns of the output once (no accumulator re-reads), and a
+# column's sum keeps its edge order: bit-identical to the unsplit exchange.  GNNB200_HALO_SLABS=1 turns it off.
+DEFAULT_HALO_SLABS = 4
 
 # Which rows travel per layer and direction ("halo = all remote rows for the uniform generator; only
 # referenced blocks for the locality generator"):
@@ -246,6 +251,7 @@ class PartitionedGraph:
         self.lo, self.hi, self.per = shard_bounds(self.num_nodes, rank, world)
         self.n_local = self.hi - self.lo
         self.chunks = max(1, min(int(chunks), self.per)) if world > 1 else 1
+        self.slabs = max(1, int(os.environ.get('GNNB200_HALO_SLABS', DEFAULT_HALO_SLABS)))
         self.rpc = (self.per + self.chunks - 1) // self.chunks            # rows per piece of one shard
         n_rows = max(self.n_local, 1)
         src, dst = edge_index[0], edge_index[1]
@@ -394,6 +400,9 @@ class PartitionedGraph:
             f = x_local.size(1)
             full = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).gather_all(x_local)
             return ops._aggregate_raw(full, rowptr, col, L.AGG_SUM, x_local, eps, None, long_rows=long_rows)
+        f = x_local.size(1)
+        if self.chunks == 1 and self.slabs > 1 and f % (4 * self.slabs) == 0 and ops.on_device(x_local):
+            return self._aggregate_column_slabs(x_local, eps, rowptr, col, long_rows)
         pieces = self.gather_pieces_async(x_local)
         out = None
         for c, (work, buf) in enumerate(pieces):
@@ -403,6 +412,29 @@ class PartitionedGraph:
                                      x_local if last else None, eps if last else None, None, out,
                                      long_rows=long_rows if self.chunks == 1 else None)
         return out
+
+
+def _aggregate_column_slabs(self, x_local: Tensor, eps: Tensor, rowptr: Tensor, col: Tensor, long_rows) -> Tensor:
+    """Dense halo exchange pipelined over column slabs (see DEFAULT_HALO_SLABS)."""
+    f, n_loc = x_local.size(1), x_local.size(0)
+    w = f // self.slabs
+    out = x_local.new_empty(n_loc, f)
+    in_flight = []
+    for c in range(self.slabs):
+        send = x_local.new_empty(self.per, w)
+        send[:n_loc].copy_(x_local[:, c * w:(c + 1) * w])
+        if n_loc < self.per:
+            send[n_loc:].zero_()
+        buf = x_local.new_empty(self.world * self.per, w)
+        in_flight.append((dist.all_gather_into_tensor(buf, send, group=self.group, async_op=True), buf))
+    for c, (work, buf) in enumerate(in_flight):
+        work.wait()                                       # the current stream waits for slab c only
+        ops._aggregate_raw(buf, rowptr, col, L.AGG_SUM, x_local[:, c * w:(c + 1) * w], eps, None,
+                           dst=out[:, c * w:(c + 1) * w], long_rows=long_rows)
+    return out
+
+
+PartitionedGraph._aggregate_column_slabs = _aggregate_column_slabs
 
 
 class _PartitionedGINAggregate(torch.autograd.Function):

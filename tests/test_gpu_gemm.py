@@ -157,9 +157,9 @@ def test_tf32_falls_back_to_ffma_only_for_illegal_layouts():
     err = _rel(got, want)
     assert 1e-6 < err < 5e-3, err               # tf32 rounding is visible: the tensor-core kernel ran
     assert ops._tma_rows(a) is ops._tma_rows(a) and ops._tma_rows(a).stride(0) == 1436          # cached, re-pitched
-    assert _rel(ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32x3']), want) < TOL_F32
+    assert _rel(ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32x3']), want) < 3e-5     # K = 1433 accumulations
     a.add_(1.0)                                 # an in-place edit invalidates the cached copy
-    assert _rel(ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32x3']), a.double().cpu() @ w.double().cpu().t()) < TOL_F32
+    assert _rel(ops.gemm(a, False, w, True, None, False, ops.PRECISIONS['tf32x3']), a.double().cpu() @ w.double().cpu().t()) < 3e-5
     w1 = torch.randn(1, 256, device=DEV)        # N = 1 (the link decoder's last layer): FFMA, fp32 class
     x = torch.randn(300, 256, device=DEV)
     assert _rel(ops.gemm(x, False, w1, True, None, False, ops.PRECISIONS['tf32']), x.double().cpu() @ w1.double().cpu().t()) < TOL_F32
@@ -184,7 +184,7 @@ def test_encoder_widths_run_on_the_tensor_cores(rows, fin, fout):
     y = lin(xd)
     y.backward(go.to(DEV))
     assert 'gnnb200_linear_x3w_f32' in ops.call_counts()
-    assert _rel(y, ref(x).detach()) < TOL_F32
+    assert _rel(y, ref(x).detach()) < (TOL_F32 if fin <= 1024 else 3e-5)     # fp32 accumulation over up to 3703 terms
     assert lin.weight.grad.shape == ref.weight.grad.shape and lin.weight.grad.is_contiguous()
     err = _rel(lin.weight.grad, ref.weight.grad)
     assert 1e-7 < err < 5e-3, err               # tf32 noise: the weight gradient came from the tensor-core kernel
@@ -295,11 +295,12 @@ def test_linear_x3w_is_fp32_class(monkeypatch, raw_hi, m, n, k):
     prec = ops.PRECISIONS['tf32_fwd3']
     want = x.double() @ w.double().t() + bias.double()
     xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
-    assert _rel(ops._linear_fwd_raw(xd, wd, bd, False, prec), want) < TOL_F32
-    assert _rel(ops._linear_fwd_raw(xd, wd, bd, True, prec, res.to(DEV)), torch.relu(want + res.double())) < TOL_F32
+    tol = TOL_F32 if k <= 1024 else 3e-5                                  # fp32 accumulation over K terms
+    assert _rel(ops._linear_fwd_raw(xd, wd, bd, False, prec), want) < tol
+    assert _rel(ops._linear_fwd_raw(xd, wd, bd, True, prec, res.to(DEV)), torch.relu(want + res.double())) < tol
     y, s, m2 = ops._linear_fwd_raw(xd, wd, bd, False, prec, None, True)
     yd = y.double().cpu()
-    assert _rel(y, want) < TOL_F32 and _rel(s, yd.sum(0)) < 1e-5 and _rel(m2, ((yd - yd.mean(0)) ** 2).sum(0)) < 1e-4
+    assert _rel(y, want) < tol and _rel(s, yd.sum(0)) < 1e-5 and _rel(m2, ((yd - yd.mean(0)) ** 2).sum(0)) < 1e-4
 
 
 def test_linear_autograd_tf32_fwd3():

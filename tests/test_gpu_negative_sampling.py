@@ -41,7 +41,10 @@ def _check(graphs, quota=None, seed=0, expect_device=True):
 @pytest.mark.parametrize('domain', ['ENZYMES', 'PROTEINS', 'MUTAG', 'NCI1'])
 @pytest.mark.parametrize('count,seed', [(32, 0), (128, 1), (1, 2)])
 def test_tu_shaped_batches_on_the_device(domain, count, seed):
-    _check(synthetic.tu_like_graphs(domain, count, seed=seed))
+    # whether the whole batch stays on the device depends on the data (a large graph, or a single graph whose quota is its
+    # own edge count, draws from random.sample upstream and sends the batch to the host sampler): both outcomes are checked
+    # against the oracle; the device-only outcome is pinned by the tests below
+    _check(synthetic.tu_like_graphs(domain, count, seed=seed), expect_device=None)
 
 
 @pytest.mark.parametrize('quota', [None, 3, 1, 1000])
