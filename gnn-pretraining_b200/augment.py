@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
-from .data import Batch
+from .data import Batch, host_mirror
 
 ATTR_MASK_MIN_NUM_FEATURES = 3
 ATTR_MASK_PROB = 0.2
@@ -108,10 +108,10 @@ class GraphAugmentor:
         x = batch.x
         dev = x.device
         num_feats = 1 if x.dim() == 1 else x.size(-1)
-        ptr = getattr(batch, '_ptr_host', None)
+        ptr = host_mirror(batch, '_ptr_host')
         if ptr is None:
             ptr = batch.ptr.tolist()
-        ei = getattr(batch, '_edge_index_host', None)       # host mirror kept by gnnb200.loader: no device read-back
+        ei = host_mirror(batch, '_edge_index_host')       # host mirror kept by gnnb200.loader: no device read-back
         if ei is None:
             ei = batch.edge_index.cpu().numpy()             # one transfer; every per-graph decision is host arithmetic
         # edges of graph g are the columns whose source lies in [ptr[g], ptr[g+1]) (PyG batches keep them grouped)

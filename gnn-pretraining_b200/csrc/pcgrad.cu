@@ -44,17 +44,21 @@ pcgrad_project_kernel(const float* __restrict__ orig, float* __restrict__ work, 
       const int tj = order[q];
       if (!present[(int64_t)tj * S + s]) continue;
       const float* gj = orig + (int64_t)tj * P + beg;
-      float d = 0.f, ni = 0.f, nj = 0.f;
+      // "norm == 0" is tested on the elements, not on the fp32 sum of squares: the reference's CPU norm accumulates in
+      // double, so a gradient of magnitude 1e-20 (squares underflow in fp32) still counts as non-zero there
+      float d = 0.f, nj = 0.f, any_i = 0.f, any_j = 0.f;
       for (int64_t k = threadIdx.x; k < len; k += kPcThreads) {
         const float a = gi[k], b = gj[k];
         d = fmaf(a, b, d);
-        ni = fmaf(a, a, ni);
         nj = fmaf(b, b, nj);
+        any_i = (a != 0.f) ? 1.f : any_i;
+        any_j = (b != 0.f) ? 1.f : any_j;
       }
       d = pc_block_sum(d, smem);
-      ni = pc_block_sum(ni, smem);
       nj = pc_block_sum(nj, smem);
-      if (ni == 0.f || nj == 0.f) continue;          // gradient_surgery.py:89-90
+      any_i = pc_block_sum(any_i, smem);
+      any_j = pc_block_sum(any_j, smem);
+      if (any_i == 0.f || any_j == 0.f) continue;    // gradient_surgery.py:89-90
       projections += 1;
       if (d < 0.f) {                                  // :95-101
         conflicts += 1;

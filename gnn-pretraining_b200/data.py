@@ -39,9 +39,27 @@ class Data:
             return None
         raise AttributeError(name)
 
+    def _structure_versions(self):
+        return tuple((k, self._t[k]._version) for k in _STRUCTURE_KEYS if isinstance(self._t.get(k), Tensor))
+
+    def host_mirror(self, name: str):
+        """A host mirror of the structure (`_ptr_host`, `_edge_index_host`, `_common_rows_host`) if it still describes the
+        tensors: an in-place edit of edge_index / ptr / batch since the mirror was taken (their `_version` moved) drops all
+        mirrors, the same rule gnnb200.graph.graph_of applies to its cached CSR."""
+        value = self.__dict__.get(name)
+        if value is None:
+            return None
+        if self.__dict__.get('_mirror_versions') != self._structure_versions():
+            for mirror in _HOST_MIRRORS + ('_mirror_versions',):
+                self.__dict__.pop(mirror, None)
+            return None
+        return value
+
     def __setattr__(self, name, value):
         if name.startswith('_'):
             self.__dict__[name] = value
+            if name in _HOST_MIRRORS:
+                self.__dict__['_mirror_versions'] = self._structure_versions()
         else:
             if name in _STRUCTURE_KEYS:            # host mirrors of the structure (Batch.from_data_list, gnnb200.loader) are stale now
                 for mirror in _HOST_MIRRORS:
@@ -83,12 +101,18 @@ class Data:
         out = type(self).__new__(type(self))
         out.__dict__.update({k: v for k, v in self.__dict__.items() if k != '_t'})
         out.__dict__['_t'] = {k: (v.clone() if isinstance(v, Tensor) else v) for k, v in self._t.items()}
+        if '_mirror_versions' in out.__dict__:
+            out.__dict__['_mirror_versions'] = out._structure_versions() if self.host_mirror('_ptr_host') is not None or \
+                self.host_mirror('_edge_index_host') is not None else None
         return out
 
     def to(self, device, non_blocking: bool = False):
+        valid = '_mirror_versions' in self.__dict__ and self.__dict__['_mirror_versions'] == self._structure_versions()
         for k, v in self._t.items():
             if isinstance(v, Tensor):
                 self._t[k] = v.to(device, non_blocking=non_blocking)
+        if '_mirror_versions' in self.__dict__:                    # the copies start their own version counters
+            self.__dict__['_mirror_versions'] = self._structure_versions() if valid else None
         return self
 
     def pin_memory(self):
@@ -99,6 +123,12 @@ class Data:
 
     def __repr__(self):
         return f"{type(self).__name__}({', '.join(f'{k}={tuple(v.shape)}' for k, v in self._t.items() if isinstance(v, Tensor))})"
+
+
+def host_mirror(obj, name: str):
+    """`obj.host_mirror(name)` for gnnb200 containers, plain attribute lookup for anything else."""
+    fn = getattr(obj, 'host_mirror', None)
+    return fn(name) if fn is not None else getattr(obj, name, None)
 
 
 class Batch(Data):

@@ -29,6 +29,11 @@ def long_rows_of(rowptr: Tensor, num_edges: int) -> Optional[Tensor]:
     return ids if ids.numel() else None
 
 
+# GNNB200_CHECK_INDICES=1: validate node ids at CSR build (one device sync per build).  The kernels dereference `col`
+# without bounds checks, like a raw CUDA gather; the PyTorch path they replace raises an index error instead.
+CHECK_INDICES = os.environ.get('GNNB200_CHECK_INDICES', '0') == '1'
+
+
 class Graph:
     """rowptr/col grouped by destination (forward gather) and, lazily, rowptr_t/col_t grouped by
     source (backward gather).  Within a row, neighbours keep the original edge order, which makes
@@ -40,6 +45,10 @@ class Graph:
         self.edge_index = edge_index.detach()
         self.num_nodes = int(num_nodes)
         self.num_edges = int(edge_index.size(1))
+        if CHECK_INDICES and self.num_edges:
+            lo, hi = int(edge_index.min()), int(edge_index.max())
+            if lo < 0 or hi >= self.num_nodes:
+                raise IndexError(f'edge_index holds node ids in [{lo}, {hi}] for a graph of {self.num_nodes} nodes')
         self.rowptr, self.col, _ = ops.csr_build(edge_index, self.num_nodes, False)   # the edge permutation is not kept
         self.long_rows = long_rows_of(self.rowptr, self.num_edges)
         self._t = None

@@ -16,6 +16,7 @@ from torch import Tensor
 from . import ops
 from . import nn as _gnn
 from .fused import GINLayerFn
+from .data import host_mirror
 from .graph import graph_of
 from .nn import BatchNormAct, FusedAwayReLU, GINConv, Linear, global_mean_pool
 
@@ -219,7 +220,7 @@ class PretrainableGNN(nn.Module):
         mask-token write / target gather are one row-scatter and one row-gather kernel."""
         with torch.no_grad():
             h0 = self.input_encoders[domain_name](batch.x)
-        bounds = getattr(batch, '_ptr_host', None) or batch.ptr.tolist()      # gnnb200.loader batches carry a host mirror
+        bounds = host_mirror(batch, '_ptr_host') or batch.ptr.tolist()      # gnnb200.loader batches carry a host mirror
         chosen = []
         for g in range(batch.num_graphs):
             lo, n = bounds[g], bounds[g + 1] - bounds[g]

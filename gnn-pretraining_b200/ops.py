@@ -1315,6 +1315,9 @@ class _NtXentTensorCore(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss: Tensor):
+        if ctx.saved is None:
+            raise L.Gnnb200Error('NT-Xent (tensor-core path): the similarity matrix was overwritten by its own gradient in '
+                                 'the first backward pass; a second backward through the same graph is not supported')
         zn, norm, sim, lse = ctx.saved
         temperature, precision = ctx.cfg
         ntxent_sim_bwd_.fn(sim, temperature, lse, g_loss)

@@ -13,6 +13,7 @@ from torch import Tensor
 
 from . import ops
 from .augment import GraphAugmentor
+from .data import host_mirror
 from .models import GRAPH_PROPERTY_DIM, PretrainableGNN
 from .nn import global_max_pool, global_mean_pool
 from .utils import batched_negative_sampling, to_undirected
@@ -145,7 +146,7 @@ class LinkPredictionTask(BasePretrainTask):
         """tasks.py:107-111: batched_negative_sampling(to_undirected(edge_index), batch, E).  Batches cut by
         gnnb200.loader carry the structure on the host: symmetrise + coalesce + sampling then run there and only the
         result is uploaded (no coalesce kernels, no count read-back, no edge-list download)."""
-        ei_host, ptr_host = getattr(batch, '_edge_index_host', None), getattr(batch, '_ptr_host', None)
+        ei_host, ptr_host = host_mirror(batch, '_edge_index_host'), host_mirror(batch, '_ptr_host')
         if ei_host is None or ptr_host is None:
             return batched_negative_sampling(edge_index=to_undirected(pos), batch=batch.batch, num_neg_samples=pos.size(1))
         if pos.size(1) == 0:
@@ -185,10 +186,10 @@ class NodeContrastiveTask(BasePretrainTask):
 
     @staticmethod
     def _common_rows(view, masks) -> Tensor:
-        planned = getattr(view, '_common_rows_host', None)
+        planned = host_mirror(view, '_common_rows_host')
         if planned is not None and planned[0] is masks:      # views made by gnnb200.augment carry the answer (host side)
             return torch.from_numpy(planned[1])
-        starts = getattr(view, '_ptr_host', None) or view.ptr.tolist()
+        starts = host_mirror(view, '_ptr_host') or view.ptr.tolist()
         rows = [torch.nonzero(m, as_tuple=False).view(-1) + starts[g] for g, m in enumerate(masks)]
         return torch.cat(rows) if rows else torch.empty(0, dtype=torch.long, device=view.x.device)
 

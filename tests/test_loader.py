@@ -232,3 +232,21 @@ def test_from_data_list_keeps_host_mirrors_until_the_structure_changes():
     assert hasattr(b, '_edge_index_host')
     b.edge_index = b.edge_index[:, :3]
     assert '_edge_index_host' not in b.__dict__ and '_ptr_host' not in b.__dict__
+
+
+def test_host_mirrors_are_dropped_after_an_in_place_edit_of_the_structure():
+    """The planners (augmentation, node masking, negative sampling) read the structure from host mirrors; an in-place edit of
+    edge_index / ptr / batch must invalidate them (the kernels see the new tensor: gnnb200.graph.graph_of checks `_version`)."""
+    from gnnb200 import synthetic
+    from gnnb200.data import Batch, Data, host_mirror
+    graphs = [Data(**g) for g in synthetic.tu_like_graphs('ENZYMES', 4, seed=1)]
+    b = Batch.from_data_list(graphs)
+    assert host_mirror(b, '_ptr_host') == b.ptr.tolist() and host_mirror(b, '_edge_index_host') is not None
+    moved = b.clone().to('cpu')
+    assert host_mirror(moved, '_ptr_host') == b.ptr.tolist()           # copies keep valid mirrors
+    b.edge_index[:, 0] = b.edge_index[:, 1]                             # in-place: the mirror no longer describes the tensor
+    assert host_mirror(b, '_edge_index_host') is None and host_mirror(b, '_ptr_host') is None
+    assert host_mirror(moved, '_edge_index_host') is not None           # the clone has its own tensors
+    b2 = Batch.from_data_list(graphs)
+    b2.edge_index = b2.edge_index.clone()                               # re-assignment drops them as before
+    assert host_mirror(b2, '_edge_index_host') is None
