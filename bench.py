@@ -396,6 +396,7 @@ def run_product(args):
     #      locality): power-law degrees + 90 % intra-block edges, the same step on the same model, device-resident ----
     gen2 = None
     if not args.no_generator2 and args.locality == 0.0 and args.skew == 0.0:
+      try:                                             # a failure here must not lose the headline line
         pending[0] = None
         slots.clear()
         torch.cuda.empty_cache()
@@ -418,6 +419,8 @@ def run_product(args):
                 'value': e * LAYERS * 2 / (g_ms / 1e3), 'unit': UNIT,
                 'halo': runner.last_halo if world > 1 else None}
         del d2, x2, ei2
+      except Exception as exc:                         # noqa: BLE001 — reported in the JSON line
+        gen2 = {'error': f'{type(exc).__name__}: {exc}'[:300]}
 
     out = None
     if rank == 0:
