@@ -33,8 +33,10 @@ DEFAULT_HALO_CHUNKS = 1
 # The dense exchange is pipelined over COLUMN slabs instead: the [rows, F] shard is all-gathered as `slabs` matrices of F/slabs
 # columns (all started asynchronously) and slab c is gathered while slabs c+1.. are still in flight.  Unlike the row pieces
 # every pass walks whole neighbour lists and writes its own columns of the output once (no accumulator re-reads), and a
-# column's sum keeps its edge order: bit-identical to the unsplit exchange.  GNNB200_HALO_SLABS=1 turns it off.
-DEFAULT_HALO_SLABS = 4
+# column's sum keeps its edge order: bit-identical to the unsplit exchange.  Measured on 2 B200s (uniform graph): 4 slabs 164.8
+# ms per step against 151.2 ms unsplit — four gathers over 256-byte row segments take 8.6 ms per pass where one gather over 1 KB
+# rows takes 5.2 ms, more than the overlap returns — so it is opt-in (GNNB200_HALO_SLABS=2 / 4).
+DEFAULT_HALO_SLABS = 1
 
 # Which rows travel per layer and direction ("halo = all remote rows for the uniform generator; only
 # referenced blocks for the locality generator"):
@@ -66,10 +68,11 @@ DEFAULT_HALO_SLABS = 4
 #   uniform graph,   8 GPUs: dense 71.4 ms, peercopy 155.0 ms (the seven pulls of a rank serialise on one stream)
 #   90 % intra-block, 8 GPUs: sparse 50.9 ms, peer 83.0 ms (remote reads inside the gather are latency-bound: 5.6 ms / pass)
 #   90 % intra-block, 2 GPUs: peer 136.9 ms, sparse 149.7 ms, dense 156.4 ms
-# hence 'auto' = the default: the overlapped sparse exchange when the ranks need less than half of the remote rows, the
-# all-gather otherwise.
+#   90 % intra-block, 2 GPUs (72 % of the remote rows needed): sparse 136.0 ms, dense 151.2 ms
+# hence 'auto' = the default: the overlapped sparse exchange when the ranks need less than 85 % of the remote rows, the
+# all-gather otherwise (uniform graph: ~100 % at 2 ranks, 96 % at 8).
 DEFAULT_HALO = 'auto'
-SPARSE_HALO_MAX_FRACTION = 0.5
+SPARSE_HALO_MAX_FRACTION = 0.85
 HALO_MODES = ('dense', 'sparse', 'sparse_overlap', 'auto', 'peer', 'peercopy')
 
 
