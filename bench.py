@@ -300,6 +300,7 @@ def run_product(args):
         stop.record()
         barrier()
     ms = start.elapsed_time(stop)
+    main_halo = runner.last_halo if world > 1 else None          # (the generator-(ii) leg below may pick another mode)
     agg_ms = [a.elapsed_time(b) for a, b in ops.AGG_TIMER]
     ops.AGG_TIMER = None
     launches = ops.launch_count()
@@ -457,7 +458,7 @@ def run_product(args):
                            {'sparse': 'halo_alltoall_sparse', 'sparse_overlap': 'halo_alltoall_sparse_overlapped_with_local_gather',
                             'peer': 'halo_read_in_gather_over_nvlink_peer_memory',
                             'peercopy': 'halo_allgather_by_copy_engines'}.get(
-                               runner.last_halo, 'halo_allgather'))},
+                               main_halo, 'halo_allgather'))},
             'clocks': clocks.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': x_host.numel() * 4 + ei_host.numel() * 8, 'd2h_bytes_per_step': 4,
