@@ -44,11 +44,13 @@ class Linear(torch.nn.Linear):
         prec = ops.PRECISIONS[self.precision or _default_precision]
         lead = x.shape[:-1]
         res = None if residual is None else residual.reshape(-1, self.out_features)
+        # a 2-D input is passed as the caller's own tensor object: the re-pitched copy of a ragged-width feature matrix
+        # (ops._tma_rows) is cached on that object and survives from step to step
+        x2 = x if x.dim() == 2 else x.reshape(-1, x.size(-1))
         if return_stats:
-            y, s, m2 = ops.linear_stats(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec, res,
-                                        bias_feeds_norm and self.training)
+            y, s, m2 = ops.linear_stats(x2, self.weight, self.bias, prec, res, bias_feeds_norm and self.training)
             return y.view(*lead, self.out_features), (s.detach(), m2.detach())
-        y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, prec, res, bias_feeds_norm and self.training)
+        y = ops.linear(x2, self.weight, self.bias, prec, res, bias_feeds_norm and self.training)
         return y.view(*lead, self.out_features)
 
 
