@@ -186,7 +186,7 @@ def partition_selfcheck(prod, dev, rank, world, halo):
             g1, eps1 = graph_of(ei, n), torch.tensor([0.25], device=dev)
             z1 = torch.cat([ops_._aggregate_raw(w, g1.rowptr, g1.col, L_.AGG_SUM, w, eps1, None),
                             ops_._aggregate_raw(w, g1.rowptr_t, g1.col_t, L_.AGG_SUM, w, eps1, None)], dim=1)
-            ref = (z1, h1.detach(), float(loss1), torch.cat([p.grad.reshape(-1) for p in m1.parameters()]))
+            ref = (z1, h1.detach(), float(loss1.detach()), torch.cat([p.grad.reshape(-1) for p in m1.parameters()]))
             out['loss_single_device'] = ref[2]
         if world > 1:
             m = fresh()
