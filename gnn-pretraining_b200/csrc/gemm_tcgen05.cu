@@ -21,7 +21,6 @@
 // epilogue.  Out-of-range rows/columns/k are zero-filled by TMA and masked in the store.
 #include <cuda.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace gnnb200 {
@@ -122,7 +121,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (SM100 UMMA): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout type [61,64): 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B
 // (the only legal layout for MN-major 32-bit operands: 128 B rows, 32 B swizzle atoms, 4-row groups).
-constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1, kLayoutSw64 = 4;
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -162,10 +161,10 @@ struct Params {
 //   X3 = 3  as 2, but the raw fp32 tiles serve as the hi operands (kind::tf32 reads only the upper 19 bits of each word —
 //           checked bit for bit by tests/test_gpu_gemm.py::test_tf32_mma_truncates_operands), so the splitter only WRITES
 //           lo(A) and the hi*hi / hi*lo(B) MMAs of a stage start as soon as TMA has landed it
-template <int BN, int X3, int BKT = BK>
+template <int BN, int X3>
 struct TileCfg {
-  static constexpr uint32_t kABytes = BM * BKT * 4;   // 16 KB at BKT = 32
-  static constexpr uint32_t kBBytes = BN * BKT * 4;
+  static constexpr uint32_t kABytes = BM * BK * 4;   // 16 KB
+  static constexpr uint32_t kBBytes = BN * BK * 4;
   static constexpr uint32_t kHiBytes = kABytes + kBBytes;
   static constexpr uint32_t kStageBytes = kHiBytes * (X3 ? 2 : 1);
   static constexpr int kEpiBytes = kEpiWarps * kEpiTileFloats * 4;
@@ -179,18 +178,13 @@ struct TileCfg {
 // XOR-swizzled 32x32 staging tile IS the SWIZZLE_128B box layout, so instead of reading it back and issuing
 // st.global the warp applies bias/ReLU on the TMEM side, and one lane hands the tile to the TMA unit
 // (cp.async.bulk.tensor store, clipped at the matrix edge by the tensor map).
-// BKT = fp32 elements per stage along K: 32 (one 128-byte swizzle span, every kernel) or 16 (64-byte rows, SWIZZLE_64B; the
-// pre-split-weight kernel only: its 96 KB stages at BKT = 32 leave a two-stage ring, 48 KB stages give four).
-template <int BN, bool A_MN, bool B_MN, int X3, bool TMA_ST = false, int BKT = BK>
+template <int BN, bool A_MN, bool B_MN, int X3, bool TMA_ST = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_blo, const Params p) {
   static_assert(!(TMA_ST && X3 != 0), "the TMA-store epilogue exists for the plain tf32 kernel only");
   static_assert(X3 < 2 || (!A_MN && !B_MN), "pre-split B: nn.Linear forward layout only (A [M,K], B [N,K])");
-  static_assert(BKT == 32 || (BKT == 16 && X3 >= 2), "16-wide K steps exist for the pre-split-weight kernel only");
-  using Cfg = TileCfg<BN, X3, BKT>;
-  constexpr uint32_t kKLayout = BKT == 32 ? kLayoutSw128 : kLayoutSw64;   // K-major tiles: 128 B or 64 B rows
-  constexpr uint32_t kKSbo = BKT == 32 ? 1024 : 512;                       // 8-row group stride
+  using Cfg = TileCfg<BN, X3>;
   constexpr int kStages = Cfg::kStages;
   constexpr uint32_t kABytes = Cfg::kABytes;
   constexpr uint32_t kBBytes = Cfg::kBBytes;
@@ -198,7 +192,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr uint32_t kStageBytes = Cfg::kStageBytes;
   constexpr int kEpi = X3 != 0 ? 4 : kEpiWarps;       // epilogue warps
   constexpr int kSplit = 6;                           // splitter warps (X3 only)
-  constexpr uint32_t kSlabBytes = BKT * 128;   // MN-major: one 32-wide slab = BKT rows x 128 B
+  constexpr uint32_t kSlabBytes = BK * 128;   // MN-major: one 32-wide slab = BK rows x 128 B
   constexpr uint32_t kIdesc = make_idesc(BN, A_MN, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -210,7 +204,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int k_blocks_total = (p.K + BKT - 1) / BKT;
+  const int k_blocks_total = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -264,7 +258,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[stage], X3 >= 2 ? kHiBytes + kBBytes : kHiBytes);
-          const int k0 = kb * BKT;
+          const int k0 = kb * BK;
           if constexpr (X3 >= 2) tma_load_2d(&map_blo, &full_bar[stage], sb + kHiBytes, k0, n0);   // lo(B) twin tile
           if (A_MN) {
 #pragma unroll
@@ -304,30 +298,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // raw tiles are the hi operands: two of the three products need nothing from the splitter warps
             const uint64_t lo_off = (uint64_t)(kHiBytes >> 4);
 #pragma unroll
-            for (int k = 0; k < BKT / UMMA_K; ++k) {
-              const uint64_t da = make_desc(sa + k * 32, 16, kKSbo, kKLayout);
-              const uint64_t db = make_desc(sb + k * 32, 16, kKSbo, kKLayout);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+              const uint64_t db = make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
               umma_tf32(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);             // hi(A) * hi(B)
               umma_tf32(d_tmem, da, db + lo_off, kIdesc, 1u);                               // hi(A) * lo(B)
             }
             mbar_wait(&split_bar[stage], phase);
             tcgen05_fence_after();
 #pragma unroll
-            for (int k = 0; k < BKT / UMMA_K; ++k) {
-              const uint64_t da = make_desc(sa + k * 32, 16, kKSbo, kKLayout);
-              const uint64_t db = make_desc(sb + k * 32, 16, kKSbo, kKLayout);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
+              const uint64_t db = make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
               umma_tf32(d_tmem, da + lo_off, db, kIdesc, 1u);                               // lo(A) * hi(B)
             }
           } else {
 #pragma unroll
-          for (int k = 0; k < BKT / UMMA_K; ++k) {
+          for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA (K=8 tf32) advances 32 B inside
             // the swizzle span.  MN-major: 32-wide slabs kSlabBytes apart (LBO), 4-row groups 512 B apart
             // (SBO); one MMA consumes 8 k-rows = 1024 B.
             const uint64_t da = A_MN ? make_desc(sa + k * 1024, kSlabBytes, 512, kLayoutSw128Base32)
-                                     : make_desc(sa + k * 32, 16, kKSbo, kKLayout);
+                                     : make_desc(sa + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t db = B_MN ? make_desc(sb + k * 1024, kSlabBytes, 512, kLayoutSw128Base32)
-                                     : make_desc(sb + k * 32, 16, kKSbo, kKLayout);
+                                     : make_desc(sb + k * 32, 16, 1024, kLayoutSw128);
             if (X3) {
               // lo tiles live kHiBytes above their hi twins (same layout): descriptor start address += kHiBytes >> 4
               const uint64_t lo_off = (uint64_t)(kHiBytes >> 4);
@@ -605,7 +599,7 @@ static EncodeTiledFn encode_fn() {
 // box {32 floats = 128 B, box_outer rows}, zero fill out of bounds; 128-byte swizzle with 16 B atoms for
 // K-major tiles and with 32 B atoms for MN-major tiles (matches the UMMA descriptor layout types).
 static int make_map(CUtensorMap* map, const float* base, long long inner, long long outer, long long ld, int box_outer,
-                    bool mn_major, int box_inner = 32) {
+                    bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return GNNB200_ETMA;
   // The driver entry point needs a current context on THIS host thread.  Threads that have only been
@@ -618,12 +612,11 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
   }
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-                           : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -637,11 +630,7 @@ static int make_map(CUtensorMap* map, const float* base, long long inner, long l
 static int pick_bn(long long N, int x3) {
   // x3 = 1 (both operands split in shared memory): 128-wide tiles (a 256-wide stage would leave one pipeline stage);
   // x3 >= 2 (B pre-split): 256-wide tiles with a two-stage ring — every A tile is split once, not once per 128 columns
-  bool wide = x3 != 1;
-  if (x3 >= 2) {                                  // TEMPORARY measurement switch (removed after round-2 call I)
-    const char* e = getenv("GNNB200_X3W_BN");
-    if (e && atoi(e) == 128) wide = false;
-  }
+  const bool wide = x3 != 1;
   if (wide && N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
   if (N % 64 == 0) return 64;
@@ -650,30 +639,30 @@ static int pick_bn(long long N, int x3) {
   return 64;
 }
 
-template <int BN, bool A_MN, bool B_MN, int X3, bool TMA_ST, int BKT = BK>
+template <int BN, bool A_MN, bool B_MN, int X3, bool TMA_ST>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mblo,
                   const Params& p, int grid, cudaStream_t stream) {
-  constexpr size_t smem = TileCfg<BN, X3, BKT>::kSmemBytes;
+  constexpr size_t smem = TileCfg<BN, X3>::kSmemBytes;
   // the attribute is per device (a process-wide flag would leave a second GPU of the same process unconfigured);
   // racing threads at worst set it twice
   static bool configured[64] = {};
   int dev = 0;
   GNNB200_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST, BKT>,
+    GNNB200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST, BKT><<<grid, kThreads, smem, stream>>>(ma, mb, mc, mblo, p);
+  gemm_tf32_kernel<BN, A_MN, B_MN, X3, TMA_ST><<<grid, kThreads, smem, stream>>>(ma, mb, mc, mblo, p);
   GNNB200_LAUNCH_CHECK();
   return GNNB200_OK;
 }
 
-template <int BN, int X3, bool TMA_ST = false, int BKT = BK>
+template <int BN, int X3, bool TMA_ST = false>
 static int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
                      const CUtensorMap& mblo, const Params& p, int grid, cudaStream_t stream) {
   if constexpr (X3 >= 2) {
-    return launch<BN, false, false, X3, TMA_ST, BKT>(ma, mb, mc, mblo, p, grid, stream);   // checked by the caller
+    return launch<BN, false, false, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);   // checked by the caller
   } else {
     if (!a_mn && !b_mn) return launch<BN, false, false, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);
     if (!a_mn && b_mn) return launch<BN, false, true, X3, TMA_ST>(ma, mb, mc, mblo, p, grid, stream);
@@ -713,15 +702,9 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, const flo
   using namespace tc;
   if (x3 >= 2 && (transa != 0 || transb == 0 || (workspace && !B_lo))) return GNNB200_EINVAL;
   const int bn = pick_bn(N, x3);
-  // 16-wide K steps (four-stage ring) for the 256-wide pre-split-weight tiles; TEMPORARY switch until measured (call I)
-  int bk = BK;
-  if (x3 == 3 && bn == 256) {
-    const char* e = getenv("GNNB200_X3W_BK");
-    if (e && atoi(e) == 16) bk = 16;
-  }
   const int m_tiles = (int)((M + BM - 1) / BM);
   const int n_tiles = (int)((N + bn - 1) / bn);
-  const int k_blocks = (int)((K + bk - 1) / bk);
+  const int k_blocks = (int)((K + BK - 1) / BK);
   // split-K only when the output has too few tiles to fill the machine and K is long
   int splits = 1;
   const long long tiles = (long long)m_tiles * n_tiles;
@@ -751,10 +734,10 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, const flo
   CUtensorMap ma, mb;
   int rc;
   if (a_mn) rc = make_map(&ma, A, M, K, lda, BK, true);            // inner = M, outer = K, box {32, BK}
-  else rc = make_map(&ma, A, K, M, lda, BM, false, bk);             // inner = K, outer = M, box {bk, 128}
+  else rc = make_map(&ma, A, K, M, lda, BM, false);                 // inner = K, outer = M, box {32, 128}
   if (rc) return rc;
   if (b_mn) rc = make_map(&mb, B, N, K, ldb, BK, true);
-  else rc = make_map(&mb, B, K, N, ldb, bn, false, bk);
+  else rc = make_map(&mb, B, K, N, ldb, bn, false);
   if (rc) return rc;
 
   Params p;
@@ -778,7 +761,7 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, const flo
   }
   CUtensorMap mblo = mb;                                 // unused unless B arrives pre-split
   if (x3 >= 2) {
-    rc = make_map(&mblo, B_lo, K, N, ldb, bn, false, bk);
+    rc = make_map(&mblo, B_lo, K, N, ldb, bn, false);
     if (rc) return rc;
   }
   if (x3 == 1) {
@@ -789,8 +772,7 @@ int gemm_tf32(const float* A, int64_t lda, int transa, const float* B, const flo
     else if (bn == 128) rc = launch_bn<128, 2>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
     else rc = launch_bn<64, 2>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
   } else if (x3 == 3) {
-    if (bn == 256 && bk == 16) rc = launch_bn<256, 3, false, 16>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
-    else if (bn == 256) rc = launch_bn<256, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
+    if (bn == 256) rc = launch_bn<256, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
     else if (bn == 128) rc = launch_bn<128, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
     else rc = launch_bn<64, 3>(a_mn, b_mn, ma, mb, mc, mblo, p, grid, stream);
   } else if (tma_st) {
