@@ -78,6 +78,7 @@ SIGNATURES = {
     'gnnb200_ce_bwd_f32': [P, I64, P, P, P, I64, I64, P, I64, P],
     'gnnb200_negsample_count_i64': [P, I64, P, P, I64, P, I64, P, P, P],
     'gnnb200_negsample_write_i64': [P, I64, P, P, I64, P, P, I64, P, P],
+    'gnnb200_host_py_sample_range': [P, P, I64, I64, P],
     'gnnb200_pcgrad_f32': [P, P, I64, I64, P, I64, P, P, P, P, P, P, P],
     'gnnb200_aggregate_peer_f32': [P, c_int, I64, P, P, I64, I64, P, I64, P, P, I64, P],
     'gnnb200_peer_publish_f32': [P, I64, I64, I64, P, I64, P],

@@ -1,4 +1,5 @@
 // C-ABI glue: version/error strings and the GEMM dispatcher (include/gnnb200.h).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gnnb200 {
@@ -99,4 +100,94 @@ extern "C" int gnnb200_linear_x3w_f32(const float* X, int64_t ldx, const float* 
                             col_m2, workspace, workspace_bytes, stream_);
   return gnnb200::gemm_tf32(X, ldx, 0, raw_hi ? W : W_hi, W_lo, ldw, 1, Y, ldy, M, N, K, bias, residual, ldr, epilogue,
                             raw_hi ? 3 : 2, col_sum, col_m2, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host helper (no device work): random.sample(range(n), k) of CPython 3.x on a COPY of the interpreter's Mersenne
+// Twister state, so that negative sampling's random branch (PyG negative_sampling -> random.sample)
+// draws exactly the reference's numbers without ~1 us of interpreter time per draw.  Follows Lib/random.py:
+//   _randbelow_with_getrandbits(m): b = m.bit_length(); r = getrandbits(b); while r >= m: r = getrandbits(b)
+//   getrandbits(b <= 32) = genrand_uint32() >> (32 - b)
+//   sample(): setsize = 21 (+ 4 ** ceil(log(3k, 4)) if k > 5); n <= setsize -> pool with swap-removal,
+//             else rejection against the set of already selected values.
+// mt[624] / *pos are Python's random.getstate()[1]; both are advanced in place.  Returns 0, or GNNB200_EINVAL /
+// GNNB200_ERANGE (n >= 2^32: the caller keeps using the interpreter).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct MT {
+  uint32_t* mt;
+  int pos;
+  uint32_t next() {
+    if (pos >= 624) {
+      static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
+      int kk;
+      uint32_t y;
+      for (kk = 0; kk < 624 - 397; kk++) {
+        y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+        mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 0x1u];
+      }
+      for (; kk < 623; kk++) {
+        y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+        mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 0x1u];
+      }
+      y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+      mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 0x1u];
+      pos = 0;
+    }
+    uint32_t y = mt[pos++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  uint64_t below(uint64_t m) {               // m >= 1, m < 2^32
+    int bits = 0;
+    for (uint64_t t = m; t; t >>= 1) ++bits;
+    uint32_t r = next() >> (32 - bits);
+    while (r >= m) r = next() >> (32 - bits);
+    return r;
+  }
+};
+}  // namespace
+
+extern "C" int gnnb200_host_py_sample_range(uint32_t* mt624, int32_t* pos, int64_t n, int64_t k, int64_t* out) {
+  if (!mt624 || !pos || n < 0 || k < 0 || k > n || (k > 0 && !out) || *pos < 0 || *pos > 624) return GNNB200_EINVAL;
+  if (n >= (1LL << 32)) return GNNB200_ERANGE;
+  if (k == 0) return GNNB200_OK;
+  MT g{mt624, *pos};
+  double setsize = 21.0;
+  if (k > 5) {
+    // 4 ** ceil(log(3k, 4)) with Python's float log: the smallest power of 4 that is >= 3k, except where the
+    // float quotient log(3k)/log(4) lands above an exact integer (it does not for 3k < 2^53: checked by the tests)
+    int e = 0;
+    long double p = 1.0L;
+    while (p < (long double)(3 * k)) { p *= 4.0L; ++e; }
+    (void)e;
+    setsize += (double)p;
+  }
+  if ((double)n <= setsize) {
+    int64_t* pool = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    if (!pool) return GNNB200_EINVAL;
+    for (int64_t i = 0; i < n; ++i) pool[i] = i;
+    for (int64_t i = 0; i < k; ++i) {
+      const uint64_t j = g.below((uint64_t)(n - i));
+      out[i] = pool[j];
+      pool[j] = pool[n - i - 1];
+    }
+    free(pool);
+  } else {
+    const size_t words = ((size_t)n + 63) / 64;
+    uint64_t* seen = (uint64_t*)calloc(words, sizeof(uint64_t));
+    if (!seen) return GNNB200_EINVAL;
+    for (int64_t i = 0; i < k; ++i) {
+      uint64_t j = g.below((uint64_t)n);
+      while (seen[j >> 6] & (1ull << (j & 63))) j = g.below((uint64_t)n);
+      seen[j >> 6] |= 1ull << (j & 63);
+      out[i] = (int64_t)j;
+    }
+    free(seen);
+  }
+  *pos = g.pos;
+  return GNNB200_OK;
 }

@@ -37,7 +37,8 @@ class GradientSurgery:
         flat = torch.zeros(T, total, dtype=torch.float32, device=self.device)
         present_host = []
         for t, name in enumerate(names):
-            model.zero_grad(set_to_none=True)
+            for _, p in named:                                         # = model.zero_grad(set_to_none=True) without its module walk
+                p.grad = None
             task_losses[name].backward(retain_graph=True)
             row = flat[t]
             have = []

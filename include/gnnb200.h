@@ -271,6 +271,11 @@ int gnnb200_negsample_write_i64(const int64_t* edge_index, int64_t num_edges, co
                                 const int32_t* edge_ptr, int64_t num_graphs, const int64_t* counts, const int64_t* offsets,
                                 int64_t total, int64_t* out, gnnb200_stream_t stream);
 
+/* Host helper, no device work: Python's random.sample(range(n), k) on a copy of the interpreter's Mersenne Twister state
+ * (random.getstate()[1] = 624 words + position), advanced in place — the random branch of PyG negative_sampling draws exactly
+ * upstream's numbers (src/pretrain/tasks.py:109-111) without interpreter time per draw.  GNNB200_ERANGE for n >= 2^32. */
+int gnnb200_host_py_sample_range(uint32_t* mt624, int32_t* pos, int64_t n, int64_t k, int64_t* out);
+
 /* ------------------------------------------------------------------------------------------
  * Head tails and loss sums (K10: src/models/heads.py:16-24,35-50; src/pretrain/tasks.py:84,120,305,336;
  * src/finetune/finetune.py's cross_entropy).  One launch each (a second, fixed-order finish launch beyond 2^19

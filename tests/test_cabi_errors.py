@@ -134,6 +134,8 @@ BAD = [
     ('gnnb200_negsample_count_i64', (D, BIG, D, D, 4, D, 10, D, D, None), L.ERANGE),
     ('gnnb200_negsample_write_i64', (D, 10, D, D, 4, D, D, -1, D, None), L.EINVAL),
     ('gnnb200_negsample_write_i64', (D, 10, D, D, 4, D, None, 10, D, None), L.EINVAL),
+    ('gnnb200_host_py_sample_range', (None, D, 10, 2, D), L.EINVAL),
+    ('gnnb200_host_py_sample_range', (D, None, 10, 2, D), L.EINVAL),
     # ---- gradient surgery ----
     ('gnnb200_pcgrad_f32', (D, D, -1, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),
     ('gnnb200_pcgrad_f32', (D, None, 2, 10, D, 2, D, D, D, D, D, D, None), L.EINVAL),

@@ -95,3 +95,22 @@ def test_link_prediction_negatives_from_the_host_mirror(domain):
     assert got.dtype == torch.long and torch.equal(got, want)
     assert np.array_equal(utils.to_undirected_host(b._edge_index_host, int(b.edge_index.max()) + 1),
                           pyg_utils.to_undirected(b.edge_index).numpy())
+
+
+def test_py_sample_range_is_random_sample_bit_for_bit():
+    """gnnb200.utils.py_sample_range (Mersenne Twister + CPython's two `sample` branches in C) against the interpreter's own
+    random.sample(range(n), k): same values, same stream position afterwards (also mid-block and across the pool / set
+    branch boundary n <= 21 + 4 ** ceil(log(3k, 4)))."""
+    chooser = random.Random(123)
+    sizes = [1, 2, 5, 6, 21, 22, 30, 100, 1000, 9900, 16405, 16406, 20000, 70000, 7_300_000, 2 ** 31 + 5, 2 ** 32 + 1]
+    for trial in range(120):
+        n = chooser.choice(sizes)
+        k = min(n, chooser.choice([0, 1, 2, 5, 6, 7, 20, 50, 4000, 11600, n if n < 50000 else 100]))
+        random.seed(trial)
+        burn = [random.random() for _ in range(trial * 7 % 700)]
+        want, after_want, gauss_want = random.sample(range(n), k), random.random(), random.gauss(0, 1)
+        random.seed(trial)
+        assert burn == [random.random() for _ in range(trial * 7 % 700)]
+        got = utils.py_sample_range(n, k)
+        assert got.dtype == np.int64 and got.tolist() == want, (n, k)
+        assert (random.random(), random.gauss(0, 1)) == (after_want, gauss_want), (n, k)
