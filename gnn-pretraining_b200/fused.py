@@ -28,8 +28,6 @@ from .graph import Graph
 # GIN layers.  Measured on B200 (profiles/r02/a_variants.md): C2 fine-tune step 271 -> 361 steps/s, C3 s4 step 10.7 -> 14.1,
 # C4 s5 step 6.9 -> 8.5.  GNNB200_NATIVE_LAYER=0 selects the per-kernel Python path.
 NATIVE_LAYER = os.environ.get('GNNB200_NATIVE_LAYER', '1') == '1'
-# EXPERIMENT (round-2 call L): BatchNorm column statistics out of the forward GEMMs' epilogue instead of a separate read pass
-GEMM_STATS = os.environ.get('GNNB200_GEMM_STATS', '0') == '1'
 
 
 def _native_usable(h: Tensor, tensors, bn1, bn2, graph, need_t: bool, precision: int = 0) -> bool:
@@ -120,15 +118,6 @@ class GINLayerFn(torch.autograd.Function):
             ctx.save_for_backward(h, eps, w1, g1, be1, w2, g2, be2, *saved)
             return out
         z = ops._aggregate_raw(h, graph.rowptr, graph.col, L.AGG_SUM, h, eps, None, long_rows=getattr(graph, 'long_rows', None))
-        if GEMM_STATS and training:
-            a1, cs, cm2 = ops._linear_fwd_raw(z, w1, b1, False, precision, None, True)
-            mean1, invstd1 = _stats_from(bn1, cs, cm2, a1.size(0))
-            r1 = ops.bn_act.fn(a1, mean1, invstd1, g1, be1, True, 0.0, 0, training, 0)
-            s, cs, cm2 = ops._linear_fwd_raw(r1, w2, b2, False, precision, h, True)
-            mean2, invstd2 = _stats_from(bn2, cs, cm2, s.size(0))
-            out = ops.bn_act.fn(s, mean2, invstd2, g2, be2, True, drop_p, seed, training, 0)
-            ctx.save_for_backward(h, eps, w1, g1, be1, w2, g2, be2, z, a1, r1, s, mean1, invstd1, mean2, invstd2)
-            return out
         a1 = ops._linear_fwd_raw(z, w1, b1, False, precision)
         mean1, invstd1 = _stats(bn1, a1, training)
         r1 = ops.bn_act.fn(a1, mean1, invstd1, g1, be1, True, 0.0, 0, training, 0)
@@ -165,15 +154,6 @@ class GINLayerFn(torch.autograd.Function):
             dh = ops._aggregate_raw(dz, rowptr_t, col_t, L.AGG_SUM, dz, eps, None, out=ds,    # ds is dead: reuse it
                                     long_rows=getattr(graph, 'long_rows_t', None))
         return (dh, deps, dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None)
-
-
-def _stats_from(bn, col_sum: Tensor, col_m2: Tensor, rows: int):
-    """(mean, invstd) from column sums / centred second moments a GEMM epilogue produced (training mode)."""
-    upd = bn.track_running_stats
-    if upd and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-    return ops.bn_stats_finalize.fn(col_sum, col_m2, rows, bn.running_mean if upd else None, bn.running_var if upd else None,
-                                    float(bn.momentum if bn.momentum is not None else 0.0), float(bn.eps))
 
 
 def _stats(bn, x: Tensor, training: bool):
