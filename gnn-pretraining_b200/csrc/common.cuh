@@ -10,11 +10,11 @@
     if (_e != cudaSuccess) return (int)_e;       \
   } while (0)
 
-// Every launch is followed by this: cudaPeekAtLastError reports launch-configuration errors
-// without clearing or synchronising.
+// Every launch is followed by this: reports launch-configuration errors without synchronising.  cudaGetLastError (not
+// Peek): a reported error is cleared, so one bad launch does not make every later call of the process fail as well.
 #define GNNB200_LAUNCH_CHECK()                   \
   do {                                           \
-    cudaError_t _e = cudaPeekAtLastError();      \
+    cudaError_t _e = cudaGetLastError();         \
     if (_e != cudaSuccess) return (int)_e;       \
   } while (0)
 

@@ -27,13 +27,19 @@ def lib():
 
 
 _raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_current_device = getattr(torch._C, '_cuda_getDevice', None) or torch.cuda.current_device
 
 
 def _stream(t: Tensor) -> int:
     """Raw cudaStream_t of torch's current stream on t's device (the C call is ~10x cheaper than building a
     torch.cuda.Stream object; it matters when a step is a few hundred tiny launches)."""
+    index = t.device.index
+    if index is not None and index != _current_device():
+        # the C entry points launch on the CURRENT device: a tensor of another GPU would be dereferenced in the wrong context
+        raise L.Gnnb200Error(f'tensor lives on cuda:{index} but the current device is cuda:{_current_device()}: '
+                             f'call under torch.cuda.device({index}) (one process per GPU sets it once)')
     if _raw_stream is not None:
-        return _raw_stream(t.device.index if t.device.index is not None else torch.cuda.current_device())
+        return _raw_stream(index if index is not None else _current_device())
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
