@@ -217,7 +217,7 @@ def partition_selfcheck(prod, dev, rank, world, halo):
                             'grad_fro': float((g - ref[3]).norm() / ref[3].norm())})
                 out['aggregation_max_rel'] = float((z_all - ref[0]).abs().max() / ref[0].abs().max())
                 # 'sparse_overlap' sums a row's local neighbours before its remote ones: fp32 rounding, not bit identity
-                exact = out['aggregation_bitwise'] or (graph.halo == 'sparse_overlap' and out['aggregation_max_rel'] < 1e-5)
+                exact = out['aggregation_bitwise'] or (graph.halo in ('sparse_overlap', 'sparse_pull') and out['aggregation_max_rel'] < 1e-5)
                 out['ok'] = bool(exact and out['fwd_max_rel'] < 1e-3 and out['grad_fro'] < 2e-2)
     finally:
         prod.DROPOUT_RATE = old_p
@@ -456,6 +456,7 @@ def run_product(args):
                        'l2_policy': 'inputs_larger_than_L2 (2.5 GB activations per layer vs 126 MB L2)',
                        'parallelism': 'single' if world == 1 else f'node_partition{world}+' + (
                            {'sparse': 'halo_alltoall_sparse', 'sparse_overlap': 'halo_alltoall_sparse_overlapped_with_local_gather',
+                            'sparse_pull': 'halo_rows_pulled_over_nvlink_peer_memory_overlapped_with_local_gather',
                             'peer': 'halo_read_in_gather_over_nvlink_peer_memory',
                             'peercopy': 'halo_allgather_by_copy_engines'}.get(
                                main_halo, 'halo_allgather'))},
@@ -923,7 +924,7 @@ def main():
     ap.add_argument('--skew', type=float, default=0.0,
                     help='> 1: power-law endpoints (1.8 ~ ogbn-products: largest hub 2.8e-4 of all edges); 0 = uniform (default)')
     ap.add_argument('--precision', default=None, choices=[None, 'f32', 'tf32', 'tf32x3', 'tf32_fwd3'])
-    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'sparse_overlap', 'auto', 'peer', 'peercopy'],
+    ap.add_argument('--halo', default=None, choices=[None, 'dense', 'sparse', 'sparse_overlap', 'sparse_pull', 'auto', 'peer', 'peercopy'],
                     help='N > 1: rows exchanged per layer (default dense = all-gather; see gnnb200/partition.py)')
     ap.add_argument('--cpu-sample', type=float, default=None, dest='cpu_sample',
                     help='fraction of the workload per CPU step (default: 1/16 for cpu_baseline; --impl reference picks up to 1/4 by time and memory)')

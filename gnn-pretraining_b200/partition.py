@@ -63,6 +63,11 @@ DEFAULT_HALO_SLABS = 1
 #              while the rows travel, and the halo gather then continues every row's sum (ACCUMULATE).  A row's sum is
 #              "local neighbours in edge order, then remote neighbours in edge order": deterministic, but a different
 #              association than the single-device edge order (fp32 rounding instead of bit identity).
+#   'sparse_pull': the same split as 'sparse_overlap', but the halo rows are not SENT: every rank publishes its shard in a
+#              peer-mapped buffer (PeerRows: one local copy + one barrier per pass) and PULLS the rows it references with a
+#              gather kernel whose "neighbour lists" have one remote row each (gnnb200_aggregate_peer_f32 over NVLink, one
+#              warp per row, every load independent) on a side stream while the local-source edges are summed — no pack
+#              kernel, no uneven all-to-all.  Same association as 'sparse_overlap' => the same bits as that mode.
 # All modes are bit-identical to each other and to the single-device kernel except 'sparse_overlap' (measured on 2 and 8
 # B200s over NCCL / CUDA IPC: tests/test_gpu_partition.py, bench.py's selfcheck).  Measured C5 steps (profiles/r02):
 #   uniform graph,   8 GPUs: dense 71.4 ms, peercopy 155.0 ms (the seven pulls of a rank serialise on one stream)
@@ -73,7 +78,7 @@ DEFAULT_HALO_SLABS = 1
 # all-gather otherwise (uniform graph: ~100 % at 2 ranks, 96 % at 8).
 DEFAULT_HALO = 'auto'
 SPARSE_HALO_MAX_FRACTION = 0.85
-HALO_MODES = ('dense', 'sparse', 'sparse_overlap', 'auto', 'peer', 'peercopy')
+HALO_MODES = ('dense', 'sparse', 'sparse_overlap', 'sparse_pull', 'auto', 'peer', 'peercopy')
 
 
 def shard_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int, int]:
@@ -109,6 +114,7 @@ class HaloPlan:
         dist.all_to_all_single(self.serve_idx, need - owner * per, output_split_sizes=self.serve_cnt,
                                input_split_sizes=self.need_cnt, group=group)
         self.halo_rows = int(need.numel())
+        self.need = need                                   # ascending global ids of the referenced remote rows
         self.col = torch.where(remote, self.n_local + torch.searchsorted(need, other), other - lo)
 
     def exchange_async(self, x_local: Tensor):
@@ -274,11 +280,12 @@ class PartitionedGraph:
             self.rowptr_t, self.col_t, _, self.plan_t = self._build_sparse(dst, src, n_rows)
             self._find_long_rows()
             return
-        if self.halo == 'sparse_overlap':
+        if self.halo in ('sparse_overlap', 'sparse_pull'):
             self.chunks = 1
             self.split, self.local_edges = self._build_split(src, dst, n_rows)
             self.split_t, _ = self._build_split(dst, src, n_rows)
             self.rowptr = self.col = self.rowptr_t = self.col_t = None
+            self._pull_stream = None
             return
         if self.halo == 'peer':
             self.chunks = 1
@@ -316,6 +323,10 @@ class PartitionedGraph:
         rowptr_l, col_l, _ = ops.csr_build(torch.stack([plan.col[near], m[near]], dim=0), n_rows, False)
         rowptr_h, col_h, _ = ops.csr_build(torch.stack([plan.col[remote] - self.n_local, m[remote]], dim=0), n_rows, False)
         plan.col = None
+        if self.halo == 'sparse_pull':                     # one-entry "neighbour lists": row i of the halo buffer = remote row need[i]
+            plan.pull_rowptr = torch.arange(plan.halo_rows + 1, dtype=torch.int32, device=o.device)
+            plan.pull_col = encode_peer_columns(plan.need, self.per).to(torch.int32)
+        plan.need = None
         plan.long_local = long_rows_of(rowptr_l, int(col_l.numel()))
         plan.long_halo = long_rows_of(rowptr_h, int(col_h.numel()))
         return (rowptr_l, col_l, rowptr_h, col_h, plan), int(m.numel())
@@ -393,6 +404,32 @@ class PartitionedGraph:
             if work is not None:
                 work.wait()
             if plan.halo_rows:
+                out = ops._aggregate_raw(halo, rowptr_h, col_h, L.AGG_SUM, None, None, None, out, long_rows=plan.long_halo)
+            return out
+        if self.halo == 'sparse_pull':
+            rowptr_l, col_l, rowptr_h, col_h, plan = self.split_t if transposed else self.split
+            f = x_local.size(1)
+            table = PeerRows.get(self.per, f, self.rank, self.world, self.group, x_local.device).publish(x_local)
+            halo = done = None
+            if plan.halo_rows and x_local.is_cuda:
+                main = torch.cuda.current_stream(x_local.device)
+                if self._pull_stream is None:
+                    self._pull_stream = torch.cuda.Stream(device=x_local.device)
+                published = torch.cuda.Event()
+                published.record(main)                                  # behind the publish copy and the barrier
+                with torch.cuda.stream(self._pull_stream):
+                    self._pull_stream.wait_event(published)
+                    halo = ops.aggregate_peer(table, f, plan.pull_rowptr, plan.pull_col, f, None, None)   # rows over NVLink ...
+                    done = torch.cuda.Event()
+                    done.record(self._pull_stream)
+            elif plan.halo_rows:
+                halo = ops.aggregate_peer(table, f, plan.pull_rowptr, plan.pull_col, f, None, None)
+            out = ops._aggregate_raw(x_local, rowptr_l, col_l, L.AGG_SUM, x_local, eps, None,             # ... while these are summed
+                                     long_rows=plan.long_local)
+            if halo is not None:
+                if done is not None:
+                    main.wait_event(done)
+                    halo.record_stream(main)
                 out = ops._aggregate_raw(halo, rowptr_h, col_h, L.AGG_SUM, None, None, None, out, long_rows=plan.long_halo)
             return out
         if self.halo == 'peer':

@@ -148,6 +148,18 @@ def _sparse_worker(rank, world, port, out_dir):
             # local neighbours first, remote neighbours second: the same sum in another association (fp32 rounding)
             assert float((a - c).abs().max()) <= 1e-5 * float(a.abs().max())
             assert torch.equal(c, auto.aggregate(x[auto.lo:auto.hi].contiguous(), eps, transposed))     # deterministic
+        # 'sparse_pull': the halo rows pulled from the owners' published buffers instead of sent; same association as
+        # 'sparse_overlap', hence the same bits; several passes exercise the two-buffer rotation and the side stream
+        pull = partition.PartitionedGraph(data['edge_index'], n, rank, world, halo='sparse_pull')
+        for it in range(4):
+            xi = torch.randn(n, 256, generator=torch.Generator().manual_seed(40 + it)).to(dev)
+            for transposed in (False, True):
+                want = auto.aggregate(xi[auto.lo:auto.hi].contiguous(), eps, transposed)
+                assert torch.equal(pull.aggregate(xi[pull.lo:pull.hi].contiguous(), eps, transposed), want), (it, transposed)
+        torch.cuda.synchronize()
+        dist.barrier()
+        for rows in list(partition.PeerRows._cache.values()):
+            rows.close()
         open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
     finally:
         dist.destroy_process_group()

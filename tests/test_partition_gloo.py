@@ -255,16 +255,20 @@ class _FakePeerDevice:
             return 0
         if name == 'gnnb200_aggregate_f32':                      # the ordinary single-buffer gather ('peercopy' ends in it)
             x, ldx, rowptr, col, n_rows, feat, mode, self_x, lds, eps, dinv, out, ldo, _ = a
-            assert mode == 0 and not dinv
+            accumulate = bool(mode & 8)                          # GNNB200_AGG_ACCUMULATE ('sparse_pull' / 'sparse_overlap' halo pass)
+            assert mode & 7 == 0 and not dinv
             rp = self._ints(rowptr, n_rows + 1, ctypes.c_int32)
             cols = self._ints(col, int(rp[-1]), ctypes.c_int32).astype(np.int64) if rp[-1] else np.zeros(0, np.int64)
             rows_x = int(cols.max()) + 1 if cols.size else 0
             xs = torch.from_numpy(self._floats(x, max(rows_x, 1) * ldx).reshape(-1, ldx)[:, :feat].copy())
             acc = torch.zeros(n_rows, feat)
+            if accumulate:
+                acc = torch.from_numpy(self._floats(out, n_rows * ldo).reshape(n_rows, ldo)[:, :feat].copy())
             acc.index_add_(0, torch.repeat_interleave(torch.arange(n_rows), torch.from_numpy(np.diff(rp)).long()),
                            xs[torch.from_numpy(cols)] if cols.size else torch.zeros(0, feat))
-            mine = torch.from_numpy(self._floats(self_x, n_rows * lds).reshape(n_rows, lds)[:, :feat].copy())
-            acc = acc + (1 + float(self._floats(eps, 1)[0])) * mine
+            if self_x:
+                mine = torch.from_numpy(self._floats(self_x, n_rows * lds).reshape(n_rows, lds)[:, :feat].copy())
+                acc = acc + (1 + float(self._floats(eps, 1)[0])) * mine
             self._floats(out, n_rows * ldo).reshape(n_rows, ldo)[:, :feat] = acc.numpy()
             return 0
         if name in ('gnnb200_peer_close', 'gnnb200_peer_free'):
@@ -316,7 +320,7 @@ def _peer_worker(rank, world, port, n, e, f, out_dir, halo='peer'):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('halo', ['peer', 'peercopy'])
+@pytest.mark.parametrize('halo', ['peer', 'peercopy', 'sparse_pull'])
 @pytest.mark.parametrize('world,n,e', [(2, 101, 700), (3, 50, 400), (2, 7, 5)])
 def test_peer_halo_host_logic(tmp_path, world, n, e, halo):
     mp.spawn(_peer_worker, args=(world, _free_port(), n, e, 8, str(tmp_path), halo), nprocs=world, join=True)
