@@ -67,7 +67,8 @@ DEFAULT_HALO_SLABS = 1
 #              peer-mapped buffer (PeerRows: one local copy + one barrier per pass) and PULLS the rows it references with a
 #              gather kernel whose "neighbour lists" have one remote row each (gnnb200_aggregate_peer_f32 over NVLink, one
 #              warp per row, every load independent) on a side stream while the local-source edges are summed — no pack
-#              kernel, no uneven all-to-all.  Same association as 'sparse_overlap' => the same bits as that mode.
+#              kernel, no uneven all-to-all.  Same association as 'sparse_overlap' => the same bits as that mode.  Measured
+#              slower (generator (ii), 8 GPUs: 67.1 vs 48.1 ms per step): SM-issued remote reads, as in 'peer'.  Opt-in.
 # All modes are bit-identical to each other and to the single-device kernel except 'sparse_overlap' (measured on 2 and 8
 # B200s over NCCL / CUDA IPC: tests/test_gpu_partition.py, bench.py's selfcheck).  Measured C5 steps (profiles/r02):
 #   uniform graph,   8 GPUs: dense 71.4 ms, peercopy 155.0 ms (the seven pulls of a rank serialise on one stream)
