@@ -76,6 +76,9 @@ def _ld(t: Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
 
 
+BYPASS_OPERAND_CACHES = False     # gnnb200.cuda_graphs: recompute splits / re-pitched copies inside a captured graph
+
+
 def _tma_rows(t: Tensor) -> Tensor:
     """`t` with a row pitch TMA can address (a multiple of 16 bytes, 16-byte aligned base): the tensor itself when it
     already is, else the [rows, cols] view of a zero-padded copy with leading dimension ceil4(cols) — same logical shape,
@@ -88,16 +91,17 @@ def _tma_rows(t: Tensor) -> Tensor:
         return t                                           # ragged width on an aligned pitch: TMA clips the box
     key = (t._version, t.data_ptr(), tuple(t.shape))
     cached = getattr(t, '_gnnb200_tma_rows', None)
-    if cached is not None and cached[0] == key:
+    if cached is not None and cached[0] == key and not BYPASS_OPERAND_CACHES:
         return cached[1]
     src = t.detach()
     pad = torch.zeros(src.size(0), (src.size(1) + 3) // 4 * 4, dtype=src.dtype, device=src.device)
     view = pad[:, : src.size(1)]
     view.copy_(src)
-    try:
-        t._gnnb200_tma_rows = (key, view)
-    except AttributeError:
-        pass
+    if not BYPASS_OPERAND_CACHES:                         # (a graph capture's buffers are only valid after a replay)
+        try:
+            t._gnnb200_tma_rows = (key, view)
+        except AttributeError:
+            pass
     return view
 
 
@@ -592,7 +596,7 @@ def split_weight(w: Tensor) -> Tuple[Optional[Tensor], Tensor]:
     (an optimizer step bumps `_version`) or re-allocated."""
     key = (w._version, w.data_ptr(), X3W_RAW_HI)
     cached = getattr(w, '_gnnb200_split', None)
-    if cached is not None and cached[0] == key:
+    if cached is not None and cached[0] == key and not BYPASS_OPERAND_CACHES:
         return cached[1], cached[2]
     src = w.detach()
     rows, pitch = src.size(0), _ld(src)
@@ -605,7 +609,8 @@ def split_weight(w: Tensor) -> Tuple[Optional[Tensor], Tensor]:
     L.check(_invoke('gnnb200_split_tf32_f32', _ptr(src), count, _ptr(hi), _ptr(lo), _stream(src)), 'split_tf32')
     if X3W_RAW_HI:
         hi = None
-    w._gnnb200_split = (key, hi, lo)
+    if not BYPASS_OPERAND_CACHES:
+        w._gnnb200_split = (key, hi, lo)
     return hi, lo
 
 
