@@ -8,6 +8,7 @@ Import name ``gnnb200`` (see /gnnb200.py); the sources live in ``gnn-pretraining
   nn.py      GINConv / global_{mean,max,add}_pool / Linear drop-ins
   models.py  InputEncoder, GINLayer, GINBackbone, heads, PretrainableGNN, FinetuneGNN
   tasks.py   the six pre-training tasks (compute_loss call surface of the reference)
+  partition.py / cuda_graphs.py   node-partitioned multi-GPU execution; CUDA-graph replay of a fixed-batch eval forward
   compat/    a ``torch_geometric`` stand-in so the reference's files run unmodified on these kernels
 """
 from . import _lib
