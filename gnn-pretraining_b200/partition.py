@@ -167,7 +167,7 @@ class PeerRows:
 
     @classmethod
     def get(cls, rows: int, feat: int, rank: int, world: int, group, device) -> 'PeerRows':
-        key = (id(group), rows, feat, rank, world, str(device))
+        key = (group, rows, feat, rank, world, str(device))      # the group object itself: an id() could be reused after a destroy
         if key not in cls._cache:
             cls._cache[key] = cls(rows, feat, rank, world, group, device)
         return cls._cache[key]
