@@ -1,15 +1,12 @@
 #!/usr/bin/env python
-"""Times the BatchNorm(+ReLU+dropout) kernels and the column statistics at the C5 shapes, first versions against the
-column-stationary variants (GNNB200_EW_V2=1, csrc/elementwise_v2.cu), and checks that the variants reproduce the
-first versions (bitwise for the elementwise kernels, to rounding for the statistics).
+"""Times the BatchNorm(+ReLU+dropout) kernels and the column statistics at the C5 shapes (L2 flushed between launches).
+The round-2 comparison of the first versions against the column-stationary kernels that are now the default is kept in
+profiles/r02/a_elementwise_v1_v2.txt.
 
-  python scripts/bench_elementwise.py [--rows 2449029] [--reps 20]
-
-The flag is read once per process, so the script re-runs itself as a child with the variable set."""
+  python scripts/bench_elementwise.py [--rows 2449029] [--reps 20]"""
 import argparse
 import json
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -79,32 +76,12 @@ def main():
     if args.child:
         print(json.dumps(measure(args.rows, args.reps)))
         return
-    res = {}
-    for name, flag in (('v1', '0'), ('v2', '1')):
-        env = dict(os.environ, GNNB200_EW_V2=flag)
-        p = subprocess.run([sys.executable, __file__, '--child', '--rows', str(args.rows), '--reps', str(args.reps)],
-                           env=env, capture_output=True, text=True)
-        if p.returncode != 0:
-            print(f'{name} failed:\n{p.stderr[-2000:]}')
-            sys.exit(1)
-        res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    print(f'{"case":<18}{"kernel":<20}{"v1 ms":>9}{"frac":>7}{"v2 ms":>9}{"frac":>7}')
-    ok = True
-    for case in res['v1']:
-        for k, a in res['v1'][case].items():
-            if k == 'checks':
-                for ck, va in a.items():
-                    vb = res['v2'][case]['checks'][ck]
-                    exact = case.endswith('colstats') is False and ck in ('y', 'y_absmax', 'dx', 'dx_absmax')
-                    same = (va == vb) if exact else abs(va - vb) <= 1e-5 * max(1.0, abs(va))
-                    ok &= same
-                    if not same:
-                        print(f'  MISMATCH {case}.{ck}: v1 {va!r} v2 {vb!r}')
-                continue
-            b = res['v2'][case][k]
-            print(f'{case:<18}{k:<20}{a["ms"]:9.3f}{a["frac_of_hbm_peak"]:7.2f}{b["ms"]:9.3f}{b["frac_of_hbm_peak"]:7.2f}')
-    print('variants reproduce the first versions' if ok else 'VARIANTS DISAGREE')
-    sys.exit(0 if ok else 1)
+    res = measure(args.rows, args.reps)
+    print(f'{"case":<18}{"kernel":<20}{"ms":>9}{"frac of HBM peak":>18}')
+    for case, entry in res.items():
+        for k, a in entry.items():
+            if k != 'checks':
+                print(f'{case:<18}{k:<20}{a["ms"]:9.3f}{a["frac_of_hbm_peak"]:18.2f}')
 
 
 if __name__ == '__main__':
